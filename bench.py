@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native JARVIS-HybridNet 3D hot path (BASELINE.json metric: 3D frame-sets/s).
+
+A step = one pass of the hot path (reprojection gather -> V2V 3D CNN -> centroid; reference:
+jarvis/hybridnet/model.py:65-88) over one batch of synthetic frame sets.  The 2D CNNs, video decode and
+CSV writing are outside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]             our arm (N>1: launched under torchrun)
+  python bench.py --impl reference ...                            the reference algorithm on host cores
+
+Workload (config.workload): BASELINE.json configs[2] — full HybridNet 3D forward, 32 frame sets per step and
+GPU, Example_Project shape (12 cameras, K=23, 128^2 heat maps, 72^3 grid).  Each rank runs an independent
+frame stream (weak scaling, no collective in the timed region); results are all-gathered once afterwards.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import jarvis_hybridnet_b200.synth as S  # noqa: E402
+
+WORKLOADS = {
+    "c3_full3d_example": dict(shape=S.EXAMPLE, batch=32),
+    "c2_micro": dict(shape=S.MICRO, batch=8),
+    "c5_stress": dict(shape=S.STRESS, batch=8),
+    "tiny": dict(shape=S.TINY, batch=4),
+}
+
+
+def v2v_flops(sh):
+    """Exact un-padded 2*MAC of V2VNet per frame set (SURVEY.md §8a layer table), by kernel family."""
+    K, h, q = sh.K, sh.h, sh.h // 2
+    M, Mq = h ** 3, q ** 3
+    f = {
+        "front_k3s2": 2 * M * K * 2 * K * 27,
+        "res_k3_2C": 6 * 2 * M * (2 * K) ** 2 * 27,
+        "pool_k2s2": 2 * Mq * 2 * K * 4 * K * 8,
+        "res_k3_4C": 2 * 2 * Mq * (4 * K) ** 2 * 27,
+        "up_convT": 2 * Mq * 4 * K * 2 * K * 8,
+        "head_1x1": 2 * M * 2 * K * K,
+    }
+    f["total"] = sum(f.values())
+    return f
+
+
+def repro_bytes(sh, s_in=4, s_out=4):
+    """Algorithmic bytes of the reprojection stage per frame set: every un-padded map read once, volume written once."""
+    return sh.ncam * sh.K * sh.hm * sh.hm * s_in + sh.K * sh.G ** 3 * s_out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def make_inputs(sh, batch, n_batches, seed=0, distinct=8):
+    """Pool of `n_batches` host batches (numpy) of `batch` frame sets each; `distinct` rendered frame sets are
+    re-used with fresh noise-free rotation so generation stays cheap.  Pool size exceeds L2 many times over."""
+    cam, intr, dist = S.make_rig(sh.ncam, seed)
+    sets = [S.make_frameset(sh, cam, intr, dist, seed * 100 + i) for i in range(distinct)]
+    batches = []
+    for nb in range(n_batches):
+        ids = [(nb * batch + i) % distinct for i in range(batch)]
+        hm = np.stack([sets[i][0] for i in ids])
+        c3 = np.stack([sets[i][1] for i in ids])
+        chm = np.stack([sets[i][2] for i in ids])
+        rep = lambda a: np.broadcast_to(a[None], (batch,) + a.shape).copy()
+        batches.append((hm, c3, chm, rep(cam), rep(intr), rep(dist)))
+    return batches, sets, (cam, intr, dist)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[1]) for r in rows if len(r) >= 9]
+        if not sm:
+            return out
+        out["sm_mhz"] = float(np.median(sm))
+        out["sm_max_mhz"] = float(rows[0][2])
+        out["samples"] = len(sm)
+        out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, n in enumerate(names):
+            if any(r[5 + i].strip().lower() == "active" for r in rows if len(r) >= 9):
+                out["reasons"].append(n)
+        return out
+
+
+def run_reference(args, wl):
+    """Reference arm: the reference's algorithm on the host cores (oracle port of repro_layer.py / v2vnet.py /
+    model.py tail), all host threads, one bounded sample of the workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import hybridnet_oracle as O
+    O.build()
+    sh = wl["shape"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cam, intr, dist = S.make_rig(sh.ncam, 0)
+    sample = max(1, min(wl["batch"], args.ref_sample))
+    sets = [S.make_frameset(sh, cam, intr, dist, i) for i in range(sample)]
+    w = S.make_v2v_weights(sh.K, 0, "he")
+
+    def step():
+        for hm, c3, chm, _ in sets:
+            O.hybrid3d_forward(w, hm, c3, chm, cam, intr, dist, sh.roi, sh.spacing)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = dict(metric="frame_sets_per_sec", value=v, unit="frame-sets/s", impl="reference", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, ncam=sh.ncam, K=sh.K, heatmap=sh.hm, grid=sh.G,
+                            frame_sets_per_step=sample),
+                cpu_baseline=dict(value=v, unit="frame-sets/s", cores=cores, kind="port",
+                                  sample=f"{sample} frame set(s) of the workload shape per step, {args.steps} steps, "
+                                         f"oracle port of the reference (C index/gather/tail + torch-CPU V2V)"),
+                e2e=dict(value=v, unit="frame-sets/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(sh, budget_s=12.0):
+    import torch
+    from oracle import hybridnet_oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cam, intr, dist = S.make_rig(sh.ncam, 0)
+    hm, c3, chm, _ = S.make_frameset(sh, cam, intr, dist, 0)
+    w = S.make_v2v_weights(sh.K, 0, "he")
+    O.hybrid3d_forward(w, hm, c3, chm, cam, intr, dist, sh.roi, sh.spacing)      # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        O.hybrid3d_forward(w, hm, c3, chm, cam, intr, dist, sh.roi, sh.spacing)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > budget_s or n >= 64:
+            break
+    return dict(value=n / dt, unit="frame-sets/s", cores=cores, kind="port",
+                sample=f"{n} frame set(s) of the workload shape in {dt:.1f} s, oracle port of the reference "
+                       f"(C index/gather/tail on {cores} threads + torch-CPU V2V)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_full3d_example", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="frame sets per step and GPU (default: workload's)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--ref-sample", type=int, default=2, help="frame sets per reference-arm step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    from jarvis_hybridnet_b200 import HybridNet3D, _lib, gather_results
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 under torch.distributed.run")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sh, B = wl["shape"], wl["batch"]
+    K_steps, W = args.steps, max(args.warmup, 0)
+
+    precision = args.precision
+    weights = S.make_v2v_weights(sh.K, 0, "he")
+    if precision == "auto":
+        try:
+            probe = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, weights, precision="bf16").cuda()
+            probe.v2vNet._get_handle()
+            precision = "bf16"
+            del probe
+        except RuntimeError:
+            precision = "fp32"
+    net = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, weights, precision=precision).cuda()
+
+    n_pool = 2
+    batches, sets, rig = make_inputs(sh, B, n_pool, seed=rank)
+    to_t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    host = [[to_t(a).pin_memory() for a in b] for b in batches]
+    devb = [[t.cuda(non_blocking=True) for t in b] for b in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput --------------------------------------------------------------
+    for i in range(W):
+        net(*devb[i % n_pool])
+    barrier()
+    clk = ClockSampler(local)
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K_steps):
+        out = net(*devb[i % n_pool])
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = clk.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * K_steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers -------------------------------------
+    for i in range(min(W, 2)):
+        net.forward_host(host[i % n_pool])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K_steps):
+        res, h2d, d2h = net.forward_host(host[i % n_pool])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e = dict(value=world * B * K_steps / e2e_s, unit="frame-sets/s", h2d_bytes_per_step=int(h2d),
+               d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * e2e_s / K_steps)
+
+    # ---- the one collective of the job: gather [N,K,4] at the end ---------------------------------
+    gather_ms = None
+    if world > 1:
+        pts, conf, _ = out
+        local_res = torch.cat([pts, conf[..., None]], 2)
+        torch.cuda.synchronize(); g0 = time.perf_counter()
+        full = gather_results(local_res, world * B)
+        torch.cuda.synchronize(); gather_ms = 1e3 * (time.perf_counter() - g0)
+        assert full.shape[0] == world * B
+
+    # ---- per-kernel device time (CUDA events inside the library) over the same steps ---------------
+    _lib.profile(True)
+    for i in range(K_steps):
+        net(*devb[i % n_pool])
+    prof = _lib.profile_collect()
+    _lib.profile(False)
+    pk = peaks()
+    fl = v2v_flops(sh)
+    kern = {k: dict(launches=n, ms_per_step=msk / K_steps) for k, (n, msk) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    s_in = 4
+    rp_ms = sum(v["ms_per_step"] for k, v in kern.items() if k in ("coarse_project_kernel", "fine_index_kernel",
+                                                                   "relayout_kernel", "gather_mean_kernel"))
+    conv_ms = sum(v["ms_per_step"] for k, v in kern.items() if "conv" in k)
+    tail_ms = sum(v["ms_per_step"] for k, v in kern.items() if "centroid" in k)
+    stages = dict(
+        reproject=dict(ms_per_step=rp_ms, algorithmic_GB_per_s=B * repro_bytes(sh, s_in, 4 if precision == "fp32" else 2) / (rp_ms * 1e-3) / 1e9 if rp_ms else None),
+        v2v_convs=dict(ms_per_step=conv_ms, algorithmic_TFLOP_per_s=B * fl["total"] / (conv_ms * 1e-3) / 1e12 if conv_ms else None),
+        tail=dict(ms_per_step=tail_ms, algorithmic_GB_per_s=B * sh.K * sh.h ** 3 * 4 / (tail_ms * 1e-3) / 1e9 if tail_ms else None),
+    )
+    top = next(iter(kern)) if kern else None
+    roofline = None
+    if top is not None:
+        per_launch_ms = prof[top][1] / prof[top][0]
+        if "conv" in top or "tc_" in top:
+            fam = dict(tc_conv_k3_2C=fl["res_k3_2C"], tc_conv_k3_4C=fl["res_k3_4C"], tc_conv_front=fl["front_k3s2"])
+            per_step = fam.get(top, fl["front_k3s2"] + fl["res_k3_2C"] + fl["res_k3_4C"] if top == "conv3d_f32_kernel<3>" else fl["total"])
+            n_per_step = prof[top][0] / K_steps
+            ach = B * per_step / n_per_step / (per_launch_ms * 1e-3) / 1e12
+            roofline = dict(kernel=top, bound="tensor", achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
+                            frac=ach / pk["bf16_sustained"], traffic=None, peak_source=pk["src"] + ", sustained bf16",
+                            algorithmic_flop_per_launch=B * per_step / n_per_step, avg_launch_ms=per_launch_ms)
+        else:
+            byts = B * repro_bytes(sh, s_in, 4 if precision == "fp32" else 2)
+            ach = byts / (per_launch_ms * 1e-3) / 1e9
+            roofline = dict(kernel=top, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                            traffic=None, peak_source=pk["src"], algorithmic_bytes_per_launch=byts, avg_launch_ms=per_launch_ms)
+
+    if rank == 0:
+        cb = None if args.no_cpu_baseline or world > 1 else cpu_baseline(sh)
+        line = dict(metric="frame_sets_per_sec", value=value, unit="frame-sets/s", n_gpus=world, steps=K_steps, warmup=W,
+                    ms_per_step=ms / K_steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16" if precision == "bf16" else "f32", data="synthetic",
+                    config=dict(workload=args.workload, ncam=sh.ncam, K=sh.K, heatmap=sh.hm, grid=sh.G,
+                                frame_sets_per_step_per_gpu=B, weights="random-init he (seed 0)",
+                                l2="inputs rotate through %d batches of %.0f MB (>> 126 MB L2)" % (n_pool, B * sh.ncam * sh.K * sh.hm ** 2 * 4 / 1e6),
+                                timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded"),
+                    clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb,
+                    stages=stages, kernels=kern, gather_ms=gather_ms)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,144 @@
+/*
+ * jarvis_hybridnet_b200.h — C ABI of the B200-native (sm_100a) 3D inference hot path of
+ * JARVIS-HybridNet:  ReprojectionLayer -> V2VNet -> softplus centroid.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own for this path;
+ * its plugin seam is attribute replacement on HybridNetBackbone after torch.ops.load_library
+ * (jarvis/prediction/jarvis3D.py:53-69).  Each entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller (PyTorch allocates);
+ *     the library never frees caller memory and allocates nothing except the packed-weights handle;
+ *   - every call is asynchronous and ordered on `stream` (pass torch.cuda.current_stream()); no call
+ *     synchronises, so all of them are CUDA-graph capturable, and re-entrant across streams/devices;
+ *   - return value: 0 on success, negative jhn_status on failure; jhn_last_error() returns a
+ *     thread-local message.  There is NO fallback: an unsupported device or shape is an error;
+ *   - B is the number of independent frame sets processed by one call (the reference always runs B=1,
+ *     jarvis/hybridnet/repro_layer.py:112-117).
+ */
+#ifndef JARVIS_HYBRIDNET_B200_H
+#define JARVIS_HYBRIDNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *jhn_stream_t;          /* == cudaStream_t */
+typedef struct jhn_v2v jhn_v2v;                    /* opaque packed V2VNet weights */
+
+enum jhn_status {
+    JHN_OK = 0,
+    JHN_ERR_ARG = -1,          /* null pointer / bad enum                      */
+    JHN_ERR_SHAPE = -2,        /* unsupported or inconsistent dimensions       */
+    JHN_ERR_ARCH = -3,         /* device is not sm_100 (B200)                  */
+    JHN_ERR_CUDA = -4,         /* a CUDA call failed (message has the detail)  */
+    JHN_ERR_WORKSPACE = -5     /* caller workspace too small or misaligned     */
+};
+
+enum jhn_precision {
+    JHN_FP32 = 0,              /* fp32 storage and FFMA arithmetic: the parity path            */
+    JHN_BF16 = 1               /* bf16 storage, tcgen05 tensor-core convolutions, fp32 accum   */
+};
+
+enum jhn_lerp_mode {           /* rounding of ATen's trilinear lerp           */
+    JHN_LERP_FMA_FIRST = 0,    /* fma(w0, a, w1*b)  — ATen CPU                                 */
+    JHN_LERP_FMA_SECOND = 1,   /* fma(w1, b, w0*a)                                             */
+    JHN_LERP_NO_FMA = 2        /* w0*a + w1*b, both products rounded                           */
+};
+
+/* Layout of the feature volume handed from the reprojection stage to V2VNet. */
+enum jhn_volume_layout {
+    JHN_VOL_NCDHW_F32 = 0,     /* [B][K][G][G][G] fp32 — the reference tensor (repro_layer.py:119) */
+    JHN_VOL_V2V_BF16 = 1       /* bf16, parity-split channel-blocked, consumed by the tensor-core
+                                  front convolution (DESIGN.md "HBM layouts")                      */
+};
+
+const char *jhn_last_error(void);
+int jhn_abi_version(void);
+/* JHN_OK iff `device` is a compute-capability 10.x part this library was built for. */
+int jhn_check_device(int device);
+
+/* Measurement aids (not part of the drop-in surface; used by bench.py):
+ *   jhn_launch_count     kernels launched by this library since load (bench.py "gpu_launches");
+ *   jhn_profile_enable   while on, every launch is bracketed by CUDA events on its stream;
+ *   jhn_profile_collect  device-sync, then "<kernel>\t<launches>\t<total_ms>\n" per kernel name into buf. */
+unsigned long long jhn_launch_count(void);
+void jhn_profile_enable(int on);
+int jhn_profile_collect(char *buf, int cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1 — replaces F.pad (jarvis/hybridnet/model.py:65-66) + ReprojectionLayer.forward
+ * (jarvis/hybridnet/repro_layer.py:110-119, :88-107, :40-85) + the /255 of model.py:72.
+ *
+ *   heatmaps        device fp32 [B][ncam][K][S][S]; S = hs if heatmaps_padded else hs-2.
+ *                   (heatmaps_padded=1 is the tensor the reference passes to reproLayer.)
+ *   cameraMatrices  device fp32 [B][ncam][4][3]      intrinsicMatrices device fp32 [B][ncam][3][3]
+ *   distortion      device fp32 [B][ncam][1][5]      center3D device i32 [B][3]
+ *   centerHM        device i32 [B][ncam][2]
+ *   hs              padded heat-map side = BOUNDING_BOX_SIZE/2 + 2 (repro_layer.py:37)
+ *   G, spacing      grid side ROI_CUBE_SIZE/GRID_SPACING (even) and GRID_SPACING in mm
+ *   post_divide     1.0f -> reference ReprojectionLayer output; 255.0f folds model.py:72
+ *   volume_out      device, layout `layout`
+ *   index_out       optional device i32 [B][ncam][G][G][G]: flat padded-pixel index y*hs+x, the
+ *                   int64 `res` of repro_layer.py:82-83 (bit-exact parity target); may be NULL
+ * ------------------------------------------------------------------------------------------------ */
+int jhn_reproject_workspace_bytes(int B, int ncam, int K, int hs, int G, int precision, size_t *bytes);
+int jhn_reproject_gather(const float *heatmaps, int heatmaps_padded,
+                         const float *cameraMatrices, const float *intrinsicMatrices,
+                         const float *distortionCoefficients,
+                         const int32_t *center3D, const int32_t *centerHM,
+                         int B, int ncam, int K, int hs, int G, float spacing,
+                         int lerp_mode, float post_divide, int precision, int layout,
+                         void *volume_out, int32_t *index_out,
+                         void *workspace, size_t workspace_bytes, jhn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2 — replaces V2VNet (jarvis/hybridnet/v2vnet.py:86-102) in eval mode.
+ *
+ * jhn_v2v_create packs the 24 checkpoint tensors (device fp32, PyTorch layouts: Conv3d
+ * [Cout][Cin][k][k][k], ConvTranspose3d [Cin][Cout][k][k][k]) in the order of
+ * jarvis_hybridnet_b200.synth.V2V_LAYERS (weight, bias per layer).  C = K key points:
+ * channel widths are K, 2K, 4K (v2vnet.py:62-96).
+ *
+ * jhn_v2v_forward: volume_in has layout `in_layout` ([B][K][G][G][G] fp32, already divided by 255, or
+ * the bf16 V2V layout written by jhn_reproject_gather); out is device fp32 [B][K][G/2][G/2][G/2]
+ * (the tensor v2vNet returns, model.py:72).
+ * ------------------------------------------------------------------------------------------------ */
+int jhn_v2v_create(const float *const *tensors, int num_tensors, int K, int precision,
+                   jhn_stream_t stream, jhn_v2v **out);
+void jhn_v2v_destroy(jhn_v2v *net);
+int jhn_v2v_workspace_bytes(const jhn_v2v *net, int B, int G, size_t *bytes);
+int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G,
+                    float *out, void *workspace, size_t workspace_bytes, jhn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3 — replaces the inline tail of HybridNetBackbone.forward (jarvis/hybridnet/model.py:73-87):
+ * softplus, sum-normalised centroid, confidence, voxel -> mm.
+ *
+ *   v2v_out   device fp32 [B][K][h][h][h]        center3D device i32 [B][3]
+ *   points    device fp32 [B][K][3] (mm)         conf device fp32 [B][K]
+ *   argmax    optional device i32 [B][K]: first flat index of the per-key-point maximum
+ * ------------------------------------------------------------------------------------------------ */
+int jhn_centroid_reduce(const float *v2v_out, int B, int K, int h, float spacing, float roi,
+                        const int32_t *center3D, float *points, float *conf, int32_t *argmax,
+                        jhn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stages 1-3 fused behind one call (model.py:65-88): heat maps in, key points out.
+ * ------------------------------------------------------------------------------------------------ */
+int jhn_hybrid3d_workspace_bytes(const jhn_v2v *net, int B, int ncam, int hs, int G, size_t *bytes);
+int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps_padded,
+                         const float *cameraMatrices, const float *intrinsicMatrices,
+                         const float *distortionCoefficients,
+                         const int32_t *center3D, const int32_t *centerHM,
+                         int B, int ncam, int hs, int G, float spacing, float roi, int lerp_mode,
+                         float *points, float *conf, int32_t *argmax,
+                         void *workspace, size_t workspace_bytes, jhn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JARVIS_HYBRIDNET_B200_H */

@@ -3,3 +3,12 @@ ReprojectionLayer -> V2VNet -> softplus centroid (reference: jarvis/hybridnet/mo
 
 Sub-modules are imported lazily so that `synth` (numpy only) is usable without torch/CUDA."""
 __version__ = "0.1.0"
+
+
+def __getattr__(name):
+    import importlib
+    table = {"ReprojectionLayer": "repro_layer", "V2VNet": "v2vnet", "HybridNet3D": "model", "accelerate": "model",
+             "centroid_tail": "model", "shard_range": "model", "gather_results": "model"}
+    if name in table:
+        return getattr(importlib.import_module("." + table[name], __name__), name)
+    raise AttributeError(name)

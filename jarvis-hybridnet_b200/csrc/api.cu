@@ -1,0 +1,264 @@
+// extern "C" surface declared in include/jarvis_hybridnet_b200.h: argument validation, workspace
+// carving and stage sequencing.  No computation lives here.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "v2v.cuh"
+
+namespace jhn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int fail(int status, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(JHN_ERR_CUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// ---- optional CUDA-event profiler (off by default; never active during graph capture) -------------
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+ProfScope::ProfScope(const char *name, cudaStream_t s) : slot(-1), st(s)
+{
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, s);
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+void ProfScope::end()
+{
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    cudaEventRecord(g_prof[slot].b, st);
+}
+
+// tensor-core side (conv_tc.cu)
+int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st);
+void tc_destroy(jhn_v2v *net);
+size_t tc_workspace(const jhn_v2v *net, int B, int G);
+int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws,
+               size_t ws_bytes, cudaStream_t st);
+
+static int check_repro_shape(int B, int ncam, int K, int hs, int G)
+{
+    if (B < 1 || ncam < 1 || K < 1 || K > KP) return fail(JHN_ERR_SHAPE, "need B>=1, ncam>=1, 1<=K<=%d (got B=%d ncam=%d K=%d)", KP, B, ncam, K);
+    if (hs < 4 || hs > 1024) return fail(JHN_ERR_SHAPE, "padded heat-map side %d out of range [4,1024]", hs);
+    if (G < 4 || (G % 4) != 0 || G > 256) return fail(JHN_ERR_SHAPE, "grid side %d must be a multiple of 4 in [4,256]", G);
+    return JHN_OK;
+}
+
+}  // namespace jhn
+
+using namespace jhn;
+
+extern "C" {
+
+const char *jhn_last_error(void) { return g_err; }
+int jhn_abi_version(void) { return 1; }
+unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+
+// Synchronises the device, then writes one line per kernel name: "<name>\t<launches>\t<total_ms>\n".
+// Returns the number of bytes written (truncated to `cap`), and clears the records.
+int jhn_profile_collect(char *buf, int cap)
+{
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    std::map<std::string, std::pair<int, double>> acc;
+    for (auto &r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto &e = acc[r.name]; e.first += 1; e.second += ms; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    std::string out;
+    for (auto &kv : acc) { char line[256]; snprintf(line, sizeof(line), "%s\t%d\t%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second); out += line; }
+    int n = (int)out.size() < cap - 1 ? (int)out.size() : (cap > 0 ? cap - 1 : 0);
+    if (buf && cap > 0) { memcpy(buf, out.data(), n); buf[n] = 0; }
+    return n;
+}
+
+int jhn_check_device(int device)
+{
+    cudaDeviceProp p;
+    JHN_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return fail(JHN_ERR_ARCH, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
+    return JHN_OK;
+}
+
+int jhn_reproject_workspace_bytes(int B, int ncam, int K, int hs, int G, int precision, size_t *bytes)
+{
+    if (!bytes) return fail(JHN_ERR_ARG, "bytes is null");
+    JHN_TRY(check_repro_shape(B, ncam, K, hs, G));
+    *bytes = reproject_workspace(B, ncam, K, hs, G, precision);
+    return JHN_OK;
+}
+
+int jhn_reproject_gather(const float *heatmaps, int heatmaps_padded, const float *cameraMatrices,
+                         const float *intrinsicMatrices, const float *distortionCoefficients,
+                         const int32_t *center3D, const int32_t *centerHM, int B, int ncam, int K, int hs, int G,
+                         float spacing, int lerp_mode, float post_divide, int precision, int layout,
+                         void *volume_out, int32_t *index_out, void *workspace, size_t workspace_bytes,
+                         jhn_stream_t stream)
+{
+    if (!heatmaps || !cameraMatrices || !intrinsicMatrices || !distortionCoefficients || !center3D || !centerHM ||
+        !volume_out || !workspace)
+        return fail(JHN_ERR_ARG, "jhn_reproject_gather: null pointer argument");
+    JHN_TRY(check_repro_shape(B, ncam, K, hs, G));
+    if (lerp_mode < 0 || lerp_mode > 2) return fail(JHN_ERR_ARG, "lerp_mode %d not in {0,1,2}", lerp_mode);
+    if (precision != JHN_FP32 && precision != JHN_BF16) return fail(JHN_ERR_ARG, "precision %d unknown", precision);
+    if (layout != JHN_VOL_NCDHW_F32 && layout != JHN_VOL_V2V_BF16) return fail(JHN_ERR_ARG, "layout %d unknown", layout);
+    if (!(post_divide > 0.f)) return fail(JHN_ERR_ARG, "post_divide must be > 0");
+    if (((uintptr_t)workspace & 255) != 0) return fail(JHN_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    ReprojectArgs a{heatmaps, heatmaps_padded ? 1 : 0, cameraMatrices, intrinsicMatrices, distortionCoefficients,
+                    center3D, centerHM, B, ncam, K, hs, G, spacing, lerp_mode, post_divide, precision, layout,
+                    volume_out, index_out};
+    return reproject_launch(a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int jhn_v2v_create(const float *const *tensors, int num_tensors, int K, int precision, jhn_stream_t stream,
+                   jhn_v2v **out)
+{
+    if (!tensors || !out) return fail(JHN_ERR_ARG, "jhn_v2v_create: null pointer argument");
+    if (num_tensors != 2 * NUM_LAYERS) return fail(JHN_ERR_SHAPE, "expected %d tensors (weight,bias x %d layers), got %d", 2 * NUM_LAYERS, NUM_LAYERS, num_tensors);
+    if (K < 1 || K > KP) return fail(JHN_ERR_SHAPE, "K=%d out of range [1,%d]", K, KP);
+    if (precision != JHN_FP32 && precision != JHN_BF16) return fail(JHN_ERR_ARG, "precision %d unknown", precision);
+    for (int i = 0; i < num_tensors; ++i)
+        if (!tensors[i]) return fail(JHN_ERR_ARG, "tensor %d is null", i);
+    int dev = 0;
+    JHN_CUDA(cudaGetDevice(&dev));
+    JHN_TRY(jhn_check_device(dev));
+    jhn_v2v *net = new (std::nothrow) jhn_v2v();
+    if (!net) return fail(JHN_ERR_CUDA, "out of host memory");
+    net->K = K; net->precision = precision; net->device = dev; net->blob = nullptr; net->tc = nullptr;
+    layer_table(K, net->desc);
+    int s = v2v_f32_pack(net, tensors, (cudaStream_t)stream);
+    if (s == JHN_OK && precision == JHN_BF16) s = tc_create(net, tensors, (cudaStream_t)stream);
+    if (s != JHN_OK) { jhn_v2v_destroy(net); return s; }
+    *out = net;
+    return JHN_OK;
+}
+
+void jhn_v2v_destroy(jhn_v2v *net)
+{
+    if (!net) return;
+    if (net->tc) tc_destroy(net);
+    if (net->blob) cudaFree(net->blob);
+    delete net;
+}
+
+static int check_v2v_shape(const jhn_v2v *net, int B, int G)
+{
+    if (!net) return fail(JHN_ERR_ARG, "net is null");
+    if (B < 1) return fail(JHN_ERR_SHAPE, "B=%d must be >= 1", B);
+    if (G < 4 || (G % 4) != 0 || G > 256) return fail(JHN_ERR_SHAPE, "grid side %d must be a multiple of 4 in [4,256]", G);
+    return JHN_OK;
+}
+
+int jhn_v2v_workspace_bytes(const jhn_v2v *net, int B, int G, size_t *bytes)
+{
+    if (!bytes) return fail(JHN_ERR_ARG, "bytes is null");
+    JHN_TRY(check_v2v_shape(net, B, G));
+    *bytes = net->precision == JHN_FP32 ? v2v_f32_workspace(net, B, G) : tc_workspace(net, B, G);
+    return JHN_OK;
+}
+
+int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out,
+                    void *workspace, size_t workspace_bytes, jhn_stream_t stream)
+{
+    JHN_TRY(check_v2v_shape(net, B, G));
+    if (!volume_in || !out || !workspace) return fail(JHN_ERR_ARG, "jhn_v2v_forward: null pointer argument");
+    if (((uintptr_t)workspace & 255) != 0) return fail(JHN_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    if (net->precision == JHN_FP32) {
+        if (in_layout != JHN_VOL_NCDHW_F32) return fail(JHN_ERR_ARG, "fp32 V2V takes the NCDHW fp32 volume");
+        return v2v_f32_forward(net, (const float *)volume_in, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+    return tc_forward(net, volume_in, in_layout, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int jhn_centroid_reduce(const float *v2v_out, int B, int K, int h, float spacing, float roi, const int32_t *center3D,
+                        float *points, float *conf, int32_t *argmax, jhn_stream_t stream)
+{
+    if (!v2v_out || !center3D || !points || !conf) return fail(JHN_ERR_ARG, "jhn_centroid_reduce: null pointer argument");
+    if (B < 1 || K < 1 || h < 1 || h > 256) return fail(JHN_ERR_SHAPE, "bad shape B=%d K=%d h=%d", B, K, h);
+    return centroid_launch(v2v_out, B, K, h, spacing, roi, center3D, points, conf, argmax, (cudaStream_t)stream);
+}
+
+static int hybrid_layout(const jhn_v2v *net) { return net->precision == JHN_BF16 ? JHN_VOL_V2V_BF16 : JHN_VOL_NCDHW_F32; }
+static size_t hybrid_volume_bytes(const jhn_v2v *net, int B, int G);
+
+int jhn_hybrid3d_workspace_bytes(const jhn_v2v *net, int B, int ncam, int hs, int G, size_t *bytes)
+{
+    if (!bytes) return fail(JHN_ERR_ARG, "bytes is null");
+    JHN_TRY(check_v2v_shape(net, B, G));
+    JHN_TRY(check_repro_shape(B, ncam, net->K, hs, G));
+    size_t v2v = 0;
+    JHN_TRY(jhn_v2v_workspace_bytes(net, B, G, &v2v));
+    const int h = G / 2;
+    *bytes = align_up(reproject_workspace(B, ncam, net->K, hs, G, net->precision), 256) +
+             align_up(hybrid_volume_bytes(net, B, G), 256) + align_up(v2v, 256) +
+             align_up((size_t)B * net->K * h * h * h * sizeof(float), 256);
+    return JHN_OK;
+}
+
+int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps_padded, const float *cameraMatrices,
+                         const float *intrinsicMatrices, const float *distortionCoefficients,
+                         const int32_t *center3D, const int32_t *centerHM, int B, int ncam, int hs, int G,
+                         float spacing, float roi, int lerp_mode, float *points, float *conf, int32_t *argmax,
+                         void *workspace, size_t workspace_bytes, jhn_stream_t stream)
+{
+    size_t need = 0;
+    JHN_TRY(jhn_hybrid3d_workspace_bytes(net, B, ncam, hs, G, &need));
+    if (!workspace || workspace_bytes < need) return fail(JHN_ERR_WORKSPACE, "hybrid3d workspace: need %zu bytes, got %zu", need, workspace_bytes);
+    if (((uintptr_t)workspace & 255) != 0) return fail(JHN_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    const int h = G / 2;
+    char *p = (char *)workspace;
+    const size_t rws = align_up(reproject_workspace(B, ncam, net->K, hs, G, net->precision), 256);
+    void *ws_r = p; p += rws;
+    void *vol = p; p += align_up(hybrid_volume_bytes(net, B, G), 256);
+    size_t v2v = 0;
+    JHN_TRY(jhn_v2v_workspace_bytes(net, B, G, &v2v));
+    void *ws_v = p; p += align_up(v2v, 256);
+    float *vout = (float *)p;
+    JHN_TRY(jhn_reproject_gather(heatmaps, heatmaps_padded, cameraMatrices, intrinsicMatrices, distortionCoefficients,
+                                 center3D, centerHM, B, ncam, net->K, hs, G, spacing, lerp_mode, 255.f, net->precision,
+                                 hybrid_layout(net), vol, nullptr, ws_r, rws, stream));
+    JHN_TRY(jhn_v2v_forward(net, vol, hybrid_layout(net), B, G, vout, ws_v, align_up(v2v, 256), stream));
+    return jhn_centroid_reduce(vout, B, net->K, h, spacing, roi, center3D, points, conf, argmax, stream);
+}
+
+}  // extern "C"
+
+namespace jhn {
+size_t tc_volume_bytes(const jhn_v2v *net, int B, int G);
+}
+static size_t hybrid_volume_bytes(const jhn_v2v *net, int B, int G)
+{
+    if (net->precision == JHN_BF16) return jhn::tc_volume_bytes(net, B, G);
+    return (size_t)B * net->K * G * G * G * sizeof(float);
+}

@@ -1,0 +1,83 @@
+// Shared host/device helpers for the sm_100a kernels of the JARVIS-HybridNet 3D hot path.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/jarvis_hybridnet_b200.h"
+
+namespace jhn {
+
+// thread-local last-error string + status helpers (api.cu)
+int fail(int status, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+void count_launch(int n = 1);
+struct ProfScope {
+    int slot; cudaStream_t st;
+    ProfScope(const char *name, cudaStream_t s);
+    void end();
+};
+
+#define JHN_CUDA(expr)                                                      \
+    do {                                                                    \
+        cudaError_t e__ = (expr);                                           \
+        if (e__ != cudaSuccess) return ::jhn::cuda_fail(e__, #expr);        \
+    } while (0)
+
+// Every kernel launch goes through this: counts it (bench.py `gpu_launches`), checks the launch, and —
+// only while jhn_profile_enable(1) is set — brackets it with CUDA events on the launching stream so
+// bench.py can report per-kernel device time without a profiler attached.
+#define JHN_LAUNCH(name, st, ...)                                           \
+    do {                                                                    \
+        ::jhn::ProfScope prof__(name, st);                                  \
+        __VA_ARGS__;                                                        \
+        prof__.end();                                                       \
+        cudaError_t e__ = cudaGetLastError();                               \
+        if (e__ != cudaSuccess) return ::jhn::cuda_fail(e__, name);         \
+        ::jhn::count_launch();                                              \
+    } while (0)
+
+#define JHN_TRY(expr)                                                       \
+    do {                                                                    \
+        int s__ = (expr);                                                   \
+        if (s__ != JHN_OK) return s__;                                      \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// bump allocator over the caller's workspace (256-byte aligned slices)
+struct Arena {
+    char *base;
+    size_t size, off;
+    Arena(void *p, size_t n) : base((char *)p), size(n), off(0) {}
+    template <typename T>
+    T *take(size_t count)
+    {
+        size_t bytes = align_up(count * sizeof(T), 256);
+        T *r = (T *)(base ? base + off : nullptr);
+        off += bytes;
+        return r;
+    }
+    bool ok() const { return off <= size; }
+};
+
+constexpr int KP = 24;   // channel pitch of the channels-last heat-map staging copy (K <= 24)
+
+// ---- stage launchers (each returns a jhn_status) -------------------------------------------------
+struct ReprojectArgs {
+    const float *heatmaps; int padded;
+    const float *cam, *intr, *dist;
+    const int32_t *center3D, *centerHM;
+    int B, ncam, K, hs, G;
+    float spacing; int lerp_mode; float post_divide;
+    int precision, layout;
+    void *volume_out; int32_t *index_out;
+};
+size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision);
+int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStream_t st);
+
+int centroid_launch(const float *v, int B, int K, int h, float spacing, float roi, const int32_t *center3D,
+                    float *points, float *conf, int32_t *argmax, cudaStream_t st);
+
+}  // namespace jhn

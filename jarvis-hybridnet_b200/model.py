@@ -1,0 +1,158 @@
+"""Host side of the 3D hot path of HybridNetBackbone.forward (jarvis/hybridnet/model.py:53-90).
+
+  accelerate(backbone)  swaps `reproLayer` / `v2vNet` of a loaded reference HybridNetBackbone for the
+                        B200 modules and rebinds `forward`, the same seam the reference's own TensorRT
+                        loader uses (jarvis/prediction/jarvis3D.py:53-69).  HybridNet, JarvisPredictor3D,
+                        predict3D, the yacs config and the .pth files are untouched.
+  HybridNet3D           the three stages behind one call (`jhn_hybrid3d_forward`) for B independent frame
+                        sets: heat maps in, key points out.  This is what bench.py times.
+  shard_range/gather_results   one replica per GPU over disjoint frame-set ranges; a single gather of
+                        [N,K,4] at the end, no collective on the hot path.
+"""
+import ctypes
+import types
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .repro_layer import ReprojectionLayer
+from .synth import V2V_LAYERS
+from .v2vnet import V2VNet
+
+
+def centroid_tail(v2v_out, spacing, roi, center3D, want_argmax=False):
+    """model.py:73-87 on [B,K,h,h,h] fp32 -> points3D [B,K,3] (mm), confidences [B,K] (, argmax [B,K])."""
+    _lib.require_cuda(v2v_out, center3D)
+    lib = _lib.load()
+    B, K, h = v2v_out.shape[0], v2v_out.shape[1], v2v_out.shape[2]
+    v = v2v_out.contiguous().float()
+    c3 = center3D.contiguous().to(torch.int32)
+    pts = torch.empty((B, K, 3), dtype=torch.float32, device=v.device)
+    conf = torch.empty((B, K), dtype=torch.float32, device=v.device)
+    am = torch.empty((B, K), dtype=torch.int32, device=v.device)
+    _lib.check(lib.jhn_centroid_reduce(_lib.dptr(v), B, K, h, float(spacing), float(roi), _lib.dptr(c3),
+                                       _lib.dptr(pts), _lib.dptr(conf), _lib.dptr(am), _lib.stream_ptr()))
+    return (pts, conf, am) if want_argmax else (pts, conf)
+
+
+def _accelerated_forward(self, imgs, img_size, centerHM, center3D, cameraMatrices, intrinsicMatrices,
+                         distortionCoefficients):
+    """Replacement for HybridNetBackbone.forward with the same signature and return tuple (model.py:53-90).
+    effTrack is still the reference module (out of scope); everything after it runs on the B200 kernels.
+    `heatmap_final` / `heatmaps_padded` are only materialised when `self.return_volumes` is True: every
+    inference caller discards them (jarvis3D.py:180)."""
+    batch_size = imgs.shape[0]
+    self.heatmap_size = (img_size / 2).int()
+    hm = self.effTrack(imgs.reshape(-1, imgs.shape[2], imgs.shape[3], imgs.shape[4]))[1]
+    hm = hm.reshape(batch_size, -1, hm.shape[1], hm.shape[2], hm.shape[3])
+    # F.pad is folded into the gather (bounds instead of a padded copy); /255 is folded as post_divide
+    vol, _ = self.reproLayer.forward_batched(hm[:1], center3D[:1], centerHM[:1], cameraMatrices[:1],
+                                             intrinsicMatrices[:1], distortionCoefficients[:1], post_divide=255.0)
+    v = self.v2vNet(vol)
+    points3D, confidences = centroid_tail(v, float(self.grid_spacing), float(self.grid_size), center3D[:1])
+    heatmap_final = heatmaps_padded = None
+    if getattr(self, "return_volumes", False):
+        heatmap_final = F.softplus(F.softplus(v))                                  # model.py:73,88
+        heatmaps_padded = F.pad(hm, [1, 1, 1, 1])                                  # model.py:65-66
+    return heatmap_final, heatmaps_padded, points3D, confidences
+
+
+def accelerate(backbone, precision="fp32", lerp_mode=_lib.LERP_FMA_FIRST, return_volumes=False):
+    """Swap the 3D stages of a reference HybridNetBackbone (already built and `load_state_dict`-ed by
+    jarvis.hybridnet.hybridnet.HybridNet, hybridnet.py:77-90) for the B200 implementation, in place."""
+    cfg = backbone.cfg
+    K = cfg.KEYPOINTDETECT.NUM_JOINTS
+    new_v2v = V2VNet(K, K, precision=precision)
+    new_v2v.load_state_dict(backbone.v2vNet.state_dict(), strict=True)
+    dev = next(backbone.v2vNet.parameters()).device
+    backbone.v2vNet = new_v2v.to(dev)
+    backbone.reproLayer = ReprojectionLayer(cfg, getattr(backbone.reproLayer, "num_cameras", None),
+                                            precision=precision, lerp_mode=lerp_mode)
+    backbone.return_volumes = return_volumes
+    backbone.forward = types.MethodType(_accelerated_forward, backbone)
+    return backbone
+
+
+class HybridNet3D(nn.Module):
+    """ReprojectionLayer -> V2VNet -> centroid for B independent frame sets through ONE C-ABI call.
+
+    forward(heatmaps [B,ncam,K,S,S] fp32 (S = BB/2 un-padded or BB/2+2 padded), center3D [B,3] i32,
+            centerHM [B,ncam,2] i32, cameraMatrices [B,ncam,4,3], intrinsicMatrices [B,ncam,3,3],
+            distortionCoefficients [B,ncam,1,5]) -> points3D [B,K,3] mm, confidences [B,K], argmax [B,K]"""
+
+    def __init__(self, K, bbox, roi, spacing, state_dict=None, precision="bf16", lerp_mode=_lib.LERP_FMA_FIRST):
+        super().__init__()
+        self.K, self.roi, self.spacing = K, roi, spacing
+        self.G = int(roi / spacing)
+        self.hs = int(bbox / 2 + 2)
+        self.lerp_mode = lerp_mode
+        self.v2vNet = V2VNet(K, K, precision=precision)
+        if state_dict is not None:
+            sd = {k[len("v2vNet."):] if k.startswith("v2vNet.") else k: torch.as_tensor(v) for k, v in state_dict.items()}
+            self.v2vNet.load_state_dict(sd, strict=True)
+        self._ws = None
+        self._host = None
+
+    def forward(self, heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients):
+        _lib.require_cuda(heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients)
+        lib = _lib.load()
+        B, ncam, K, S, _ = heatmaps.shape
+        if K != self.K or S not in (self.hs, self.hs - 2):
+            raise RuntimeError(f"heat maps {tuple(heatmaps.shape)} do not match K={self.K}, hs={self.hs}")
+        net = self.v2vNet._get_handle()
+        need = _lib.c_size_t()
+        _lib.check(lib.jhn_hybrid3d_workspace_bytes(net, B, ncam, self.hs, self.G, need))
+        if self._ws is None or self._ws.numel() < need.value or self._ws.device != heatmaps.device:
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=heatmaps.device)
+        dev = heatmaps.device
+        pts = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
+        conf = torch.empty((B, K), dtype=torch.float32, device=dev)
+        am = torch.empty((B, K), dtype=torch.int32, device=dev)
+        f = lambda t: t.contiguous().float()
+        i = lambda t: t.contiguous().to(torch.int32)
+        hm, cam, intr, dist, c3, chm = f(heatmaps), f(cameraMatrices), f(intrinsicMatrices), \
+            f(distortionCoefficients), i(center3D), i(centerHM)
+        _lib.check(lib.jhn_hybrid3d_forward(net, _lib.dptr(hm), int(S == self.hs), _lib.dptr(cam), _lib.dptr(intr),
+                                            _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm), B, ncam, self.hs, self.G,
+                                            float(self.spacing), float(self.roi), self.lerp_mode, _lib.dptr(pts),
+                                            _lib.dptr(conf), _lib.dptr(am), _lib.dptr(self._ws), self._ws.numel(),
+                                            _lib.stream_ptr()))
+        return pts, conf, am
+
+    def forward_host(self, host_inputs):
+        """End-to-end call with HOST (pinned) tensors: H2D copies of the six inputs, the fused forward,
+        and a D2H read of [B,K,4] (x,y,z,confidence) into pinned memory.  Returns (result, h2d_bytes, d2h_bytes)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        d = [t.to(dev, non_blocking=True) for t in host_inputs]
+        pts, conf, _ = self.forward(*d)
+        res = torch.cat([pts, conf[..., None]], dim=2)
+        if self._host is None or self._host.shape != res.shape:
+            self._host = torch.empty(res.shape, dtype=torch.float32, pin_memory=True)
+        self._host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h2d = sum(t.numel() * t.element_size() for t in host_inputs)
+        return self._host, h2d, res.numel() * 4
+
+
+# ---------------------------------------------------------------------------------- multi-GPU sharding
+def shard_range(n_items, rank, world_size):
+    """Contiguous block of frame-set indices owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n_items, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_results(local, n_items, group=None):
+    """All-gather per-rank [n_local,K,4] results into [n_items,K,4] in frame-set order.  The only
+    communication of a sharded run; uses the default process group (NCCL on GPUs, gloo in CPU tests)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_items, r, world) for r in range(world)]
+    max_n = max(e - s for s, e in sizes)
+    pad = torch.zeros((max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[: e - s] for p, (s, e) in zip(parts, sizes)], dim=0)

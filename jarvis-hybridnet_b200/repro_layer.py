@@ -1,0 +1,91 @@
+"""ReprojectionLayer — drop-in for jarvis.hybridnet.repro_layer.ReprojectionLayer (repro_layer.py:11-119),
+backed by the sm_100a reprojection kernels through `jhn_reproject_gather`.
+
+Same constructor `(cfg, num_cameras=None)`, same attributes (`grid`, `grid_size`, `grid_spacing`,
+`boxsize`, `heatmap_size`, `num_cameras`) and the same `forward(heatmaps, center, centerHM,
+cameraMatrices, intrinsicMatrices, distortionCoefficients) -> [1,K,G,G,G]` contract, including the
+reference's behaviour of reading only batch element 0 (repro_layer.py:112-117)."""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class ReprojectionLayer(nn.Module):
+    def __init__(self, cfg, num_cameras=None, precision="fp32", lerp_mode=_lib.LERP_FMA_FIRST):
+        super().__init__()
+        self.cfg = cfg
+        self.grid_spacing = cfg.HYBRIDNET.GRID_SPACING
+        self.boxsize = cfg.HYBRIDNET.ROI_CUBE_SIZE
+        self.grid_size = int(cfg.HYBRIDNET.ROI_CUBE_SIZE / cfg.HYBRIDNET.GRID_SPACING)      # :18-19
+        self.num_cameras = num_cameras if num_cameras else cfg.HYBRIDNET.NUM_CAMERAS         # :21-24
+        self.heatmap_size = int(cfg.KEYPOINTDETECT.BOUNDING_BOX_SIZE / 2 + 2)                # :37
+        self.precision = {"fp32": _lib.FP32, "bf16": _lib.BF16}[precision]
+        self.lerp_mode = lerp_mode
+        self._grid = None
+        self._ws = None
+
+    @property
+    def grid(self):
+        """Static half-resolution grid [h,h,h,3] in mm (repro_layer.py:26-36), closed form; the kernels
+        recompute it in registers and never read this tensor."""
+        if self._grid is None:
+            h = int(self.grid_size / 2)
+            half = int(self.grid_size / 2 / 2)
+            a = torch.arange(h, dtype=torch.float32) - half
+            g = torch.stack(torch.meshgrid(a, a, a, indexing="ij"), dim=3)
+            dev = "cuda" if torch.cuda.is_available() else "cpu"
+            self._grid = (g * self.grid_spacing * 2).to(dev)
+        return self._grid
+
+    def _workspace(self, nbytes, device):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _run(self, heatmaps, center, centerHM, cam, intr, dist, post_divide=1.0, want_index=False):
+        """heatmaps [B,ncam,K,S,S] with S == heatmap_size (padded) or heatmap_size-2 (un-padded)."""
+        _lib.require_cuda(heatmaps, center, centerHM, cam, intr, dist)
+        lib = _lib.load()
+        B, ncam, K, S, S2 = heatmaps.shape
+        hs, G = self.heatmap_size, self.grid_size
+        if S != S2 or S not in (hs, hs - 2):
+            raise RuntimeError(f"heat maps are {S}x{S2}; expected {hs} (padded) or {hs - 2} per side")
+        hm = heatmaps.contiguous().float()
+        cam = cam.contiguous().float(); intr = intr.contiguous().float(); dist = dist.contiguous().float()
+        c3 = center.contiguous().to(torch.int32); chm = centerHM.contiguous().to(torch.int32)
+        if cam.shape[:2] != (B, ncam) or chm.shape != (B, ncam, 2) or c3.shape != (B, 3):
+            raise RuntimeError("calibration / centre tensors do not match heat maps [B,ncam,...]")
+        need = _lib.c_size_t()
+        _lib.check(lib.jhn_reproject_workspace_bytes(B, ncam, K, hs, G, self.precision, need))
+        ws = self._workspace(need.value, hm.device)
+        vol = torch.empty((B, K, G, G, G), dtype=torch.float32, device=hm.device)
+        idx = torch.empty((B, ncam, G, G, G), dtype=torch.int32, device=hm.device) if want_index else None
+        _lib.check(lib.jhn_reproject_gather(_lib.dptr(hm), int(S == hs), _lib.dptr(cam), _lib.dptr(intr),
+                                            _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm), B, ncam, K, hs, G,
+                                            float(self.grid_spacing), self.lerp_mode, float(post_divide),
+                                            self.precision, _lib.VOL_NCDHW_F32, _lib.dptr(vol), _lib.dptr(idx),
+                                            _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+        return vol, idx
+
+    def reprojectPoints(self, x, cameraMatrices, intrinsicMatrices, distortionCoefficients, centerHM):
+        """int64 [ncam,G,G,G] flat padded-pixel indices, as repro_layer.py:40-85.  `x` is `self.grid + center`
+        like the reference passes; the integer centre is read back from its zero voxel."""
+        half = int(self.grid_size / 2 / 2)
+        center = x[half, half, half].round().to(torch.int32)[None]
+        ncam = cameraMatrices.shape[0]
+        dummy = torch.zeros((1, ncam, 1, self.heatmap_size, self.heatmap_size), device=x.device)
+        _, idx = self._run(dummy, center, centerHM[None], cameraMatrices[None], intrinsicMatrices[None],
+                           distortionCoefficients[None], want_index=True)
+        return idx[0].long()
+
+    def forward(self, heatmaps, center, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients):
+        vol, _ = self._run(heatmaps[:1], center[:1], centerHM[:1], cameraMatrices[:1], intrinsicMatrices[:1],
+                           distortionCoefficients[:1])
+        return vol
+
+    def forward_batched(self, heatmaps, center, centerHM, cameraMatrices, intrinsicMatrices,
+                        distortionCoefficients, post_divide=1.0, want_index=False):
+        """All B frame sets in one launch sequence -> ([B,K,G,G,G] fp32, optional int32 indices)."""
+        return self._run(heatmaps, center, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients,
+                         post_divide, want_index)
