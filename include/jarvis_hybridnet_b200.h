@@ -114,6 +114,13 @@ int jhn_v2v_workspace_bytes(const jhn_v2v *net, int B, int G, size_t *bytes);
 int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G,
                     float *out, void *workspace, size_t workspace_bytes, jhn_stream_t stream);
 
+/* Test aid (bf16 networks only): run ONE convolution of V2VNet on the tensor cores.  `in` is device fp32
+ * NCDHW of the layer's input, `out` device fp32 NCDHW of its raw output (bias added, before InstanceNorm).
+ * `layer` indexes synth.V2V_LAYERS; D is the layer's output grid side (input side for the transposed conv). */
+int jhn_v2v_debug_layer_workspace_bytes(const jhn_v2v *net, int layer, int B, int D, size_t *bytes);
+int jhn_v2v_debug_layer(const jhn_v2v *net, int layer, const float *in, int B, int D, float *out,
+                        void *workspace, size_t workspace_bytes, jhn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 3 — replaces the inline tail of HybridNetBackbone.forward (jarvis/hybridnet/model.py:73-87):
  * softplus, sum-normalised centroid, confidence, voxel -> mm.

@@ -25,6 +25,8 @@ SYMBOLS = {
     "jhn_v2v_destroy": (None, [_P]),
     "jhn_v2v_workspace_bytes": (c_int, [_P, c_int, c_int, POINTER(c_size_t)]),
     "jhn_v2v_forward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "jhn_v2v_debug_layer_workspace_bytes": (c_int, [_P, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "jhn_v2v_debug_layer": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P, c_size_t, _P]),
     "jhn_centroid_reduce": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
     "jhn_hybrid3d_workspace_bytes": (c_int, [_P, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "jhn_hybrid3d_forward": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float,

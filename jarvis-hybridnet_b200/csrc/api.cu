@@ -63,6 +63,9 @@ size_t tc_workspace(const jhn_v2v *net, int B, int G);
 int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws,
                size_t ws_bytes, cudaStream_t st);
 
+int tc_debug_layer(const jhn_v2v *net, int l, const float *in, int B, int D, float *out, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_debug_workspace(const jhn_v2v *net, int l, int B, int D);
+
 static int check_repro_shape(int B, int ncam, int K, int hs, int G)
 {
     if (B < 1 || ncam < 1 || K < 1 || K > KP) return fail(JHN_ERR_SHAPE, "need B>=1, ncam>=1, 1<=K<=%d (got B=%d ncam=%d K=%d)", KP, B, ncam, K);
@@ -199,6 +202,22 @@ int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, in
         return v2v_f32_forward(net, (const float *)volume_in, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream);
     }
     return tc_forward(net, volume_in, in_layout, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int jhn_v2v_debug_layer_workspace_bytes(const jhn_v2v *net, int layer, int B, int D, size_t *bytes)
+{
+    if (!net || !bytes || !net->tc) return fail(JHN_ERR_ARG, "debug layer needs a JHN_BF16 network");
+    if (layer < 0 || layer >= NUM_LAYERS || B < 1 || D < 2 || D > 61) return fail(JHN_ERR_SHAPE, "bad layer/B/D");
+    *bytes = tc_debug_workspace(net, layer, B, D);
+    return JHN_OK;
+}
+
+int jhn_v2v_debug_layer(const jhn_v2v *net, int layer, const float *in, int B, int D, float *out, void *workspace,
+                        size_t workspace_bytes, jhn_stream_t stream)
+{
+    if (!net || !in || !out || !workspace) return fail(JHN_ERR_ARG, "jhn_v2v_debug_layer: null pointer argument");
+    if (B < 1 || D < 2 || D > 61) return fail(JHN_ERR_SHAPE, "bad B/D");
+    return tc_debug_layer(net, layer, in, B, D, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int jhn_centroid_reduce(const float *v2v_out, int B, int K, int h, float spacing, float roi, const int32_t *center3D,

@@ -1,14 +1,888 @@
-// Stage 2, bf16 tensor-core path (tcgen05 / TMEM / TMA).  Placeholder until the kernels land: every
-// entry point fails loudly, there is no fallback to the fp32 path.
+// Stage 2, bf16 throughput path: V2VNet (jarvis/hybridnet/v2vnet.py:12-102) as implicit GEMMs on the
+// 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// Data layout ("BP", blocked + padded), chosen so that EVERY filter tap of a 3-D convolution is a plain
+// 16-byte-granular shift of one shared-memory tile:
+//     act[b][j][zp][pp][8]   bf16,  j = channel/8,  zp in [0,D+2),  pp = yp*(D+2)+xp in [0,(D+2)^2)
+// i.e. for each 8-channel chunk the zero-padded volume is a flat array of 16-byte voxels.  A GEMM row
+// block is 128 consecutive padded positions of one z-plane; the input window of tap (dz,dy,dx) is the
+// same flat array shifted by dy*(D+2)+dx positions in plane z+dz.  A TMA box [KC chunks][PB positions]
+// (PB = 128 + halo) lands in smem as [chunk][position][8] which IS the canonical no-swizzle K-major UMMA
+// operand layout (8 rows x 16 B core matrices, SBO = 128 B between row groups, LBO = PB*16 B between the
+// two K-chunks of one K=16 MMA) for any start row -> the 9 in-plane taps are 9 descriptors into one tile,
+// and the tile is fetched from L2 once per plane instead of once per tap.  Pad positions produce garbage
+// rows that the epilogue replaces by zeros, which keeps the zero border of the output tensor intact.
+// Stride-2 convolutions read a parity-split ("PS") copy [b][8 sub-volumes][j][zp][pp][8] of their input in
+// which every tap is again a unit-stride shift; ConvTranspose3d(k2,s2) is 8 independent 1x1x1 GEMMs whose
+// epilogue scatters to the 8 output parities.
+//
+// Kernel: persistent, warp-specialised, one CTA per SM.
+//     warp 0     TMA producer (one elected lane): activation boxes (+ weight slabs when not resident)
+//     warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M=128, N=Cout_pad, K=16
+//     warps 2-5  epilogue: tcgen05.ld -> bias -> pad mask -> bf16 store (coalesced 512 B per chunk) and
+//                per-channel sum / sum-of-squares for the following InstanceNorm (fused statistics)
+// Weights of the C->C 3x3x3 layers (124 KB bf16) stay resident in shared memory for the CTA's lifetime.
+// The work of a layer is a "stage program" (TcProgram) built on the host: per tile a list of TMA boxes and,
+// per box, the taps (smem row offset, weight index) to issue against it.
+#include <cuda.h>
+
+#include <vector>
+
 #include "v2v.cuh"
 
 namespace jhn {
-int tc_create(jhn_v2v *, const float *const *, cudaStream_t) { return fail(JHN_ERR_ARG, "bf16 tensor-core path not built yet"); }
-void tc_destroy(jhn_v2v *) {}
-size_t tc_workspace(const jhn_v2v *, int, int) { return 0; }
-size_t tc_volume_bytes(const jhn_v2v *, int, int) { return 0; }
-int tc_forward(const jhn_v2v *, const void *, int, int, int, float *, void *, size_t, cudaStream_t)
+
+// ------------------------------------------------------------------------------------------------
+// program description shared by host and device
+// ------------------------------------------------------------------------------------------------
+enum { EPI_RAW = 0, EPI_CONVT = 1, EPI_HEAD = 2 };
+constexpr int MAX_STAGES = 12, MAX_TAPS = 9, TILE_M = 128;
+
+struct TcTap { int16_t aoff, widx; };                 // row offset inside the box; weight tap index
+struct TcStage {
+    int16_t chunk0;                                   // first input chunk of the box (per sample)
+    int16_t dz;                                       // plane offset of the box relative to output z
+    int32_t pos_off;                                  // first position of the box relative to tile p0
+    int16_t ntaps, wtap0;                             // taps issued against this box; first weight tap
+    TcTap taps[MAX_TAPS];
+};
+struct TcProgram {
+    int nstages, KC, NOUT, PB, resident, ntaps_total, epi, tile_taps;
+    int stage_bytes_a, stage_bytes, nslots;           // smem ring geometry (host computed)
+    int w_bytes;                                      // resident weight bytes (0 if streamed)
+    TcStage st[MAX_STAGES];
+};
+
+struct TcLaunch {
+    const __nv_bfloat16 *w;                           // [tap][KC][NOUT][8] bf16
+    const float *bias;                                // [NOUT] fp32 (zero padded)
+    void *out;                                        // BP bf16 (RAW/CONVT) or NCDHW fp32 (HEAD)
+    float *stats;                                     // [B][NOUT][2] (sum, sumsq) or null
+    int B, D;                                         // samples, grid side of the GEMM-row positions
+    int CJ_in;                                        // chunks per sample in the input tensor (TMA dim 3)
+    int CJ_out;                                       // chunks per sample in the output tensor
+    int NT;                                           // tiles per z-plane
+    int total_tiles;                                  // B * D * NT * tile_taps
+    int Kout;                                         // real output channels (HEAD)
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one()
 {
-    return fail(JHN_ERR_ARG, "bf16 tensor-core path not built yet");
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n.reg .pred P1;\nLAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: 8-row x 16-byte core matrices;
+// LBO = byte stride between the two K-chunks of one MMA, SBO = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int N)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the implicit-GEMM kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 192;
+constexpr int EPI_TILE_FLOATS = 32 * 17;
+
+struct TileCoord { int b, z, pt, tap; };
+__device__ __forceinline__ TileCoord decode_tile(int t, const TcLaunch &L, int tile_taps)
+{
+    TileCoord c;
+    c.tap = t % tile_taps; t /= tile_taps;
+    c.pt = t % L.NT; t /= L.NT;
+    c.z = t % L.D;
+    c.b = t / L.D;
+    return c;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcProgram P, const TcLaunch L)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Wp = L.D + 2, PP = Wp * Wp;
+    const int tap_bytes = P.KC * P.NOUT * 16;
+
+    // ---- carve shared memory -----------------------------------------------------------------
+    uint8_t *w_smem = smem;                                            // resident weights
+    uint8_t *ring = smem + P.w_bytes;                                  // nslots x stage_bytes
+    float *epi_tiles = reinterpret_cast<float *>(ring + (size_t)P.nslots * P.stage_bytes);
+    float *bias_s = epi_tiles + 4 * EPI_TILE_FLOATS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 128);
+    uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *wbar = bars + 20;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
+
+    // contiguous tile range of this CTA
+    const int t_begin = (int)((long long)L.total_tiles * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)L.total_tiles * (blockIdx.x + 1) / gridDim.x);
+    const uint32_t tmem_cols = (2 * P.NOUT <= 32) ? 32 : (2 * P.NOUT <= 64) ? 64 : (2 * P.NOUT <= 128) ? 128 : 256;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.nslots; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
+        mbar_init(smem_u32(wbar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 128; i += TC_THREADS) bias_s[i] = i < P.NOUT ? L.bias[i] : 0.f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =================================== TMA producer ===================================
+        if (elect_one()) {
+            if (P.resident) {
+                mbar_expect_tx(smem_u32(wbar), (uint32_t)P.w_bytes);
+                for (int off = 0; off < P.w_bytes; off += 32768) {
+                    const int n = min(32768, P.w_bytes - off);
+                    bulk_load(smem_u32(w_smem + off), reinterpret_cast<const uint8_t *>(L.w) + off, n, smem_u32(wbar));
+                }
+            }
+            int slot = 0; uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const TileCoord c = decode_tile(t, L, P.tile_taps);
+                const int p0 = Wp + 1 + c.pt * TILE_M;
+                for (int s = 0; s < P.nstages; ++s) {
+                    const TcStage &S = P.st[s];
+                    mbar_wait(smem_u32(empty + slot), phase ^ 1);
+                    const uint32_t fb = smem_u32(full + slot);
+                    uint8_t *dst = ring + (size_t)slot * P.stage_bytes;
+                    uint32_t bytes = (uint32_t)(P.KC * P.PB * 16);
+                    if (!P.resident) bytes += (uint32_t)(S.ntaps * tap_bytes);
+                    mbar_expect_tx(fb, bytes);
+                    tma_load_4d(smem_u32(dst), &tmap, fb, 0, p0 + S.pos_off, c.z + S.dz, c.b * L.CJ_in + S.chunk0);
+                    if (!P.resident)
+                        bulk_load(smem_u32(dst + P.stage_bytes_a),
+                                  reinterpret_cast<const uint8_t *>(L.w) + (size_t)S.wtap0 * tap_bytes,
+                                  (uint32_t)(S.ntaps * tap_bytes), fb);
+                    if (++slot == P.nslots) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =================================== MMA issuer ======================================
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_bf16(P.NOUT);
+            const uint32_t lbo_a = (uint32_t)P.PB * 16, lbo_b = (uint32_t)P.NOUT * 16;
+            if (P.resident) mbar_wait(smem_u32(wbar), 0);
+            int slot = 0; uint32_t phase = 0;
+            int ab = 0; uint32_t aphase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const TileCoord c = decode_tile(t, L, P.tile_taps);
+                mbar_wait(smem_u32(tempty + ab), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * P.NOUT);
+                uint32_t acc = 0;
+                for (int s = 0; s < P.nstages; ++s) {
+                    const TcStage &S = P.st[s];
+                    mbar_wait(smem_u32(full + slot), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(ring + (size_t)slot * P.stage_bytes);
+                    for (int k = 0; k < S.ntaps; ++k) {
+                        const uint32_t a_tap = a0 + (uint32_t)S.taps[k].aoff * 16;
+                        const int widx = P.tile_taps > 1 ? c.tap : S.taps[k].widx;
+                        const uint32_t b_tap = P.resident ? smem_u32(w_smem) + (uint32_t)(widx * tap_bytes)
+                                                          : a0 + (uint32_t)P.stage_bytes_a + (uint32_t)(k * tap_bytes);
+                        for (int kc = 0; kc < P.KC; kc += 2) {
+                            tc_mma_bf16(d_tmem, umma_desc(a_tap + kc * lbo_a, lbo_a, 128),
+                                        umma_desc(b_tap + kc * lbo_b, lbo_b, 128), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc_commit(smem_u32(empty + slot));               // frees the smem slot when the MMAs retire
+                    if (++slot == P.nslots) { slot = 0; phase ^= 1; }
+                }
+                tc_commit(smem_u32(tfull + ab));                     // accumulator ready for the epilogue
+                if (++ab == 2) { ab = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // =================================== epilogue warps =================================
+        const int wq = warp & 3;                                     // TMEM lane quarter this warp may read
+        const int m = wq * 32 + lane;                                // GEMM row == position offset in the tile
+        float *tile = epi_tiles + (warp - 2) * EPI_TILE_FLOATS;
+        const int col = lane & 15, which = lane >> 4;                // statistics ownership
+        float acc_stat[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int stat_b = -1;
+        int ab = 0; uint32_t aphase = 0;
+        const size_t plane16 = (size_t)PP;                           // 16-byte units per z-plane
+        for (int t = t_begin; t < t_end; ++t) {
+            const TileCoord c = decode_tile(t, L, P.tile_taps);
+            if (L.stats && c.b != stat_b) {
+                if (stat_b >= 0) {
+#pragma unroll
+                    for (int ci = 0; ci < 6; ++ci)
+                        if (ci * 16 < P.NOUT) { atomicAdd(L.stats + ((size_t)stat_b * P.NOUT + ci * 16 + col) * 2 + which, acc_stat[ci]); acc_stat[ci] = 0.f; }
+                }
+                stat_b = c.b;
+            }
+            const int p = Wp + 1 + c.pt * TILE_M + m;
+            const int yp = p / Wp, xp = p - yp * Wp;
+            const bool valid = xp >= 1 && xp <= L.D && yp >= 1 && yp <= L.D;
+            mbar_wait(smem_u32(tfull + ab), aphase);
+            tc_fence_after();
+#pragma unroll
+            for (int ci = 0; ci < 6; ++ci) {
+                const int c0 = ci * 16;
+                if (c0 < P.NOUT) {
+                    uint32_t r[16];
+                    tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ab * P.NOUT + c0), r);
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = valid ? __uint_as_float(r[i]) + bias_s[c0 + i] : 0.f;
+                    if (P.epi == EPI_HEAD) {
+                        if (valid) {
+                            float *o = reinterpret_cast<float *>(L.out);
+                            const size_t nv = (size_t)L.D * L.D * L.D;
+                            const size_t vox = ((size_t)c.z * L.D + (yp - 1)) * L.D + (xp - 1);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < L.Kout) o[((size_t)c.b * L.Kout + c0 + i) * nv + vox] = v[i];
+                        }
+                    } else {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            pk[i] = *reinterpret_cast<uint32_t *>(&h2);
+                        }
+                        uint4 *o = reinterpret_cast<uint4 *>(L.out);
+                        const int j = c0 >> 3;
+                        if (P.epi == EPI_RAW) {
+                            if (p < PP) {
+                                const size_t base = (((size_t)c.b * L.CJ_out + j) * Wp + (c.z + 1)) * plane16 + p;
+                                o[base] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                o[base + (size_t)Wp * plane16] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            }
+                        } else if (valid) {                           // EPI_CONVT: scatter to output parity c.tap
+                            const int D2 = 2 * L.D, Wp2 = D2 + 2;
+                            const int a = c.tap >> 2, bq = (c.tap >> 1) & 1, cq = c.tap & 1;
+                            const size_t plane2 = (size_t)Wp2 * Wp2;
+                            const size_t pos2 = (size_t)(2 * (yp - 1) + bq + 1) * Wp2 + (2 * (xp - 1) + cq + 1);
+                            const size_t base = (((size_t)c.b * L.CJ_out + j) * Wp2 + (2 * c.z + a + 1)) * plane2 + pos2;
+                            o[base] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            o[base + (size_t)Wp2 * plane2] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
+                        if (L.stats) {                                 // column sums through a padded smem tile
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) tile[lane * 17 + i] = v[i];
+                            __syncwarp();
+                            float s = 0.f;
+                            for (int rr = 0; rr < 32; ++rr) { const float x = tile[rr * 17 + col]; s += which ? x * x : x; }
+                            acc_stat[ci] += s;
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(tempty + ab));
+            if (++ab == 2) { ab = 0; aphase ^= 1; }
+        }
+        if (L.stats && stat_b >= 0) {
+#pragma unroll
+            for (int ci = 0; ci < 6; ++ci)
+                if (ci * 16 < P.NOUT) atomicAdd(L.stats + ((size_t)stat_b * P.NOUT + ci * 16 + col) * 2 + which, acc_stat[ci]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// helper kernels of the bf16 path (all elementwise / HBM-bound)
+// ------------------------------------------------------------------------------------------------
+// pack PyTorch fp32 weights to [tap][KC][NOUT][8] bf16 (zero padded); ci runs over groups*8*KC_g
+__global__ void tc_pack_weights_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int cout, int cin,
+                                       int taps, int transposed, int KC, int NOUT)
+{
+    const int n = taps * KC * NOUT * 8;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int i = e & 7; int r = e >> 3;
+    const int co = r % NOUT; r /= NOUT;
+    const int j = r % KC;
+    const int t = r / KC;
+    const int ci = j * 8 + i;
+    float v = 0.f;
+    if (co < cout && ci < cin) v = transposed ? src[((size_t)ci * cout + co) * taps + t] : src[((size_t)co * cin + ci) * taps + t];
+    dst[e] = __float2bfloat16_rn(v);
+}
+
+__global__ void tc_pad_bias_kernel(const float *__restrict__ src, float *__restrict__ dst, int cout, int NOUT)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NOUT) dst[i] = i < cout ? src[i] : 0.f;
+}
+
+// zero everything of a BP/PS tensor that no kernel writes: planes 0 and D+1, rows 0 and D+1, columns 0 and D+1
+__global__ void __launch_bounds__(128)
+tc_zero_border_kernel(uint4 *__restrict__ t, int D)
+{
+    const int Wp = D + 2, PP = Wp * Wp;
+    const int zp = blockIdx.x % Wp;
+    uint4 *plane = t + ((size_t)blockIdx.y * Wp + zp) * PP;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    if (zp == 0 || zp == Wp - 1) {
+        for (int p = threadIdx.x; p < PP; p += blockDim.x) plane[p] = z4;
+    } else {
+        for (int p = threadIdx.x; p < Wp; p += blockDim.x) { plane[p] = z4; plane[(size_t)(Wp - 1) * Wp + p] = z4; }
+        for (int y = threadIdx.x; y < Wp; y += blockDim.x) { plane[(size_t)y * Wp] = z4; plane[(size_t)y * Wp + Wp - 1] = z4; }
+    }
+}
+
+int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st)
+{
+    JHN_LAUNCH("tc_zero_border_kernel", st,
+               tc_zero_border_kernel<<<dim3(D + 2, chunks_total), 128, 0, st>>>((uint4 *)tensor, D));
+    return JHN_OK;
+}
+
+// InstanceNorm (from the fused sum / sum-of-squares) [+ residual] [ReLU] [+ skip], in place on a BP tensor;
+// optionally also writes the parity-split copy the following stride-2 convolution reads.
+__global__ void __launch_bounds__(256)
+tc_norm_act_kernel(uint4 *__restrict__ x, const float *__restrict__ stats, const uint4 *__restrict__ residual,
+                   const uint4 *__restrict__ post_add, uint4 *__restrict__ ps_out, int relu, int D, int CJ, int NOUT,
+                   float inv_count, float eps)
+{
+    const int nv = D * D * D;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const int bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
+    const int z = v / (D * D), r = v - z * D * D, y = r / D, xq = r - y * D;
+    const int Wp = D + 2;
+    const size_t o = (((size_t)bj * Wp + z + 1) * Wp + y + 1) * Wp + xq + 1;
+    const uint4 raw = x[o];
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t rs[4] = {0, 0, 0, 0}, pa[4] = {0, 0, 0, 0};
+    if (residual) { const uint4 t = residual[o]; rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w; }
+    if (post_add) { const uint4 t = post_add[o]; pa[0] = t.x; pa[1] = t.y; pa[2] = t.z; pa[3] = t.w; }
+    uint32_t outw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float f[2] = {__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u)};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = j * 8 + 2 * i + e;
+            const float sum = stats[((size_t)b * NOUT + c) * 2], sq = stats[((size_t)b * NOUT + c) * 2 + 1];
+            const float mean = sum * inv_count;
+            const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
+            float yv = (f[e] - mean) * rsqrtf(var + eps);
+            if (residual) yv += e ? __uint_as_float(rs[i] & 0xffff0000u) : __uint_as_float(rs[i] << 16);
+            if (relu) yv = fmaxf(yv, 0.f);
+            if (post_add) yv += e ? __uint_as_float(pa[i] & 0xffff0000u) : __uint_as_float(pa[i] << 16);
+            f[e] = yv;
+        }
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[0], f[1]);
+        outw[i] = *reinterpret_cast<uint32_t *>(&h2);
+    }
+    const uint4 res = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    x[o] = res;
+    if (ps_out) {                                                     // [b][s][j][zp][pp] on the D/2 grid
+        const int Dh = D / 2, Wh = Dh + 2;
+        const int s = ((z & 1) * 2 + (y & 1)) * 2 + (xq & 1);
+        const size_t po = ((((size_t)b * 8 + s) * CJ + j) * Wh + (z >> 1) + 1) * Wh * Wh + (size_t)((y >> 1) + 1) * Wh + (xq >> 1) + 1;
+        ps_out[po] = res;
+    }
+}
+
+// NCDHW fp32 [B][C][G^3] -> PS bf16 [b][s][j][zp][pp][8] on the G/2 grid (entry for jhn_v2v_forward with fp32 input)
+__global__ void __launch_bounds__(256)
+tc_ncdhw_to_ps_kernel(const float *__restrict__ in, uint4 *__restrict__ out, int C, int G, int CJ)
+{
+    const size_t nv = (size_t)G * G * G;
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const int bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
+    const int I = (int)(v / ((size_t)G * G)), r = (int)(v - (size_t)I * G * G), J = r / G, Kz = r - J * G;
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c0 = j * 8 + 2 * i;
+        const float a = c0 < C ? in[((size_t)b * C + c0) * nv + v] : 0.f;
+        const float bb = c0 + 1 < C ? in[((size_t)b * C + c0 + 1) * nv + v] : 0.f;
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+        pk[i] = *reinterpret_cast<uint32_t *>(&h2);
+    }
+    const int Dh = G / 2, Wh = Dh + 2;
+    const int s = ((I & 1) * 2 + (J & 1)) * 2 + (Kz & 1);
+    const size_t po = ((((size_t)b * 8 + s) * CJ + j) * Wh + (I >> 1) + 1) * Wh * Wh + (size_t)((J >> 1) + 1) * Wh + (Kz >> 1) + 1;
+    out[po] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// BP bf16 -> NCDHW fp32 (debug / per-layer parity tests)
+__global__ void __launch_bounds__(256)
+tc_bp_to_ncdhw_kernel(const uint4 *__restrict__ in, float *__restrict__ out, int C, int D, int CJ)
+{
+    const int nv = D * D * D;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const int bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
+    const int z = v / (D * D), r = v - z * D * D, y = r / D, xq = r - y * D;
+    const int Wp = D + 2;
+    const uint4 raw = in[(((size_t)bj * Wp + z + 1) * Wp + y + 1) * Wp + xq + 1];
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c0 = j * 8 + 2 * i;
+        if (c0 < C) out[((size_t)b * C + c0) * nv + v] = __uint_as_float(w[i] << 16);
+        if (c0 + 1 < C) out[((size_t)b * C + c0 + 1) * nv + v] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// NCDHW fp32 -> BP bf16 interior (debug / per-layer parity tests)
+__global__ void __launch_bounds__(256)
+tc_ncdhw_to_bp_kernel(const float *__restrict__ in, uint4 *__restrict__ out, int C, int D, int CJ)
+{
+    const int nv = D * D * D;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const int bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
+    const int z = v / (D * D), r = v - z * D * D, y = r / D, xq = r - y * D;
+    const int Wp = D + 2;
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c0 = j * 8 + 2 * i;
+        const float a = c0 < C ? in[((size_t)b * C + c0) * nv + v] : 0.f;
+        const float bb = c0 + 1 < C ? in[((size_t)b * C + c0 + 1) * nv + v] : 0.f;
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+        pk[i] = *reinterpret_cast<uint32_t *>(&h2);
+    }
+    out[(((size_t)bj * Wp + z + 1) * Wp + y + 1) * Wp + xq + 1] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }
+static inline int tiles_per_plane(int D) { return cdiv((long long)(D - 1) * (D + 2) + D, TILE_M); }
+
+struct TcLayer {
+    TcProgram prog;
+    __nv_bfloat16 *w;
+    float *bias;
+    int cin_pad, cout_pad, cout;
+    size_t smem_bytes;
+};
+
+struct TcNet {
+    TcLayer layer[NUM_LAYERS];
+    void *blob;
+    int max_smem;
+};
+
+// Build the stage program of one layer for output/position grid side D.
+// kind: 0 = k3 s1 (BP in), 1 = k3 s2 (PS in), 2 = k2 s2 (PS in), 3 = convT k2 s2 (BP in), 4 = 1x1x1 (BP in)
+static int build_program(TcProgram &P, int kind, int cin_pad, int cout_pad, int D, int max_smem)
+{
+    memset(&P, 0, sizeof(P));
+    const int Wp = D + 2;
+    P.KC = cin_pad / 8;
+    P.NOUT = cout_pad;
+    P.tile_taps = 1;
+    P.epi = EPI_RAW;
+    const int tap_bytes = P.KC * P.NOUT * 16;
+    auto stage = [&](int chunk0, int dz, int pos_off) -> TcStage & {
+        TcStage &S = P.st[P.nstages++];
+        S.chunk0 = (int16_t)chunk0; S.dz = (int16_t)dz; S.pos_off = pos_off; S.ntaps = 0; S.wtap0 = 0;
+        return S;
+    };
+    auto tap = [&](TcStage &S, int aoff, int widx) {
+        if (S.ntaps == 0) S.wtap0 = (int16_t)widx;
+        S.taps[S.ntaps].aoff = (int16_t)aoff; S.taps[S.ntaps].widx = (int16_t)widx; S.ntaps++;
+    };
+    if (kind == 0) {
+        P.ntaps_total = 27;
+        const bool resident = (size_t)27 * tap_bytes + 4 * ((size_t)P.KC * (TILE_M + 2 * Wp + 2) * 16) + 16384 <= (size_t)max_smem;
+        P.resident = resident ? 1 : 0;
+        if (resident) {                       // one box per z-plane, 9 in-plane taps each
+            P.PB = TILE_M + 2 * Wp + 2;
+            for (int dz = 0; dz < 3; ++dz) {
+                TcStage &S = stage(0, dz, -(Wp + 1));
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx) tap(S, (Wp + 1) + (dy - 1) * Wp + (dx - 1), (dz * 3 + dy) * 3 + dx);
+            }
+        } else {                              // weights streamed with the activations: one box per (dz,dy) row
+            P.PB = TILE_M + 2;
+            for (int dz = 0; dz < 3; ++dz)
+                for (int dy = 0; dy < 3; ++dy) {
+                    TcStage &S = stage(0, dz, (dy - 1) * Wp - 1);
+                    for (int dx = 0; dx < 3; ++dx) tap(S, dx, (dz * 3 + dy) * 3 + dx);
+                }
+        }
+    } else if (kind == 1) {                   // k3 s2 p1 on the parity-split input
+        P.ntaps_total = 27; P.resident = 1; P.PB = TILE_M + Wp + 1;
+        for (int s = 0; s < 8; ++s) {
+            const int pz = s >> 2, py = (s >> 1) & 1, px = s & 1;
+            for (int dz = (pz ? 0 : 1); dz <= 1; ++dz) {
+                const int tz = pz ? (dz == 0 ? 0 : 2) : 1;
+                TcStage &S = stage(s * P.KC, dz, -(Wp + 1));
+                for (int ty = 0; ty < 3; ++ty) {
+                    if ((ty == 1) != (py == 0)) continue;
+                    for (int tx = 0; tx < 3; ++tx) {
+                        if ((tx == 1) != (px == 0)) continue;
+                        tap(S, (Wp + 1) + (ty == 0 ? -Wp : 0) + (tx == 0 ? -1 : 0), (tz * 3 + ty) * 3 + tx);
+                    }
+                }
+            }
+        }
+    } else if (kind == 2) {                   // k2 s2 p0 on the parity-split input: 8 sub-volumes, one tap each
+        P.ntaps_total = 8; P.resident = 1; P.PB = TILE_M;
+        for (int s = 0; s < 8; ++s) { TcStage &S = stage(s * P.KC, 1, 0); tap(S, 0, s); }
+    } else if (kind == 3) {                   // ConvTranspose k2 s2: tile index carries the output parity
+        P.ntaps_total = 8; P.resident = 1; P.PB = TILE_M; P.tile_taps = 8; P.epi = EPI_CONVT;
+        TcStage &S = stage(0, 1, 0); tap(S, 0, 0);
+    } else {                                  // 1x1x1 head
+        P.ntaps_total = 1; P.resident = 1; P.PB = TILE_M; P.epi = EPI_HEAD;
+        TcStage &S = stage(0, 1, 0); tap(S, 0, 0);
+    }
+    int max_taps = 0;
+    for (int s = 0; s < P.nstages; ++s) max_taps = max_taps > P.st[s].ntaps ? max_taps : P.st[s].ntaps;
+    P.stage_bytes_a = (int)align_up((size_t)P.KC * P.PB * 16, 128);
+    P.stage_bytes = P.stage_bytes_a + (P.resident ? 0 : (int)align_up((size_t)max_taps * tap_bytes, 128));
+    P.w_bytes = P.resident ? (int)align_up((size_t)P.ntaps_total * tap_bytes, 128) : 0;
+    const int fixed = P.w_bytes + 4 * EPI_TILE_FLOATS * 4 + 128 * 4 + 256 + 1024;
+    int slots = (max_smem - fixed) / P.stage_bytes;
+    if (slots > 8) slots = 8;
+    if (slots < 2) return fail(JHN_ERR_SHAPE, "tensor-core conv: tile does not fit shared memory (grid side %d)", D);
+    P.nslots = slots;
+    return JHN_OK;
+}
+
+static size_t program_smem(const TcProgram &P)
+{
+    return (size_t)P.w_bytes + (size_t)P.nslots * P.stage_bytes + 4 * EPI_TILE_FLOATS * 4 + 128 * 4 + 256 + 1024;
+}
+
+static const int kLayerKind[NUM_LAYERS] = {1, 0, 0, 2, 0, 0, 3, 0, 0, 0, 0, 4};
+
+int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st)
+{
+    if (!encode_fn()) return fail(JHN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    int dev = 0, max_smem = 0;
+    JHN_CUDA(cudaGetDevice(&dev));
+    JHN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    JHN_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TcNet *tc = new TcNet();
+    tc->blob = nullptr; tc->max_smem = max_smem;
+    net->tc = tc;
+    size_t total = 0;
+    for (int l = 0; l < NUM_LAYERS; ++l) {
+        const LayerDesc &d = net->desc[l];
+        TcLayer &T = tc->layer[l];
+        T.cin_pad = pad16(d.cin); T.cout_pad = pad16(d.cout); T.cout = d.cout;
+        const int taps = d.ks * d.ks * d.ks;
+        total += align_up((size_t)taps * T.cin_pad * T.cout_pad * 2, 256) + align_up((size_t)T.cout_pad * 4, 256);
+    }
+    JHN_CUDA(cudaMalloc(&tc->blob, total));
+    char *p = (char *)tc->blob;
+    for (int l = 0; l < NUM_LAYERS; ++l) {
+        const LayerDesc &d = net->desc[l];
+        TcLayer &T = tc->layer[l];
+        const int taps = d.ks * d.ks * d.ks;
+        T.w = (__nv_bfloat16 *)p; p += align_up((size_t)taps * T.cin_pad * T.cout_pad * 2, 256);
+        T.bias = (float *)p; p += align_up((size_t)T.cout_pad * 4, 256);
+        const int n = taps * T.cin_pad * T.cout_pad;
+        JHN_LAUNCH("tc_pack_weights_kernel", st,
+                   tc_pack_weights_kernel<<<cdiv(n, 256), 256, 0, st>>>(tensors[2 * l], T.w, d.cout, d.cin, taps, d.transposed,
+                                                                        T.cin_pad / 8, T.cout_pad));
+        JHN_LAUNCH("tc_pad_bias_kernel", st,
+                   tc_pad_bias_kernel<<<1, 128, 0, st>>>(tensors[2 * l + 1], T.bias, d.cout, T.cout_pad));
+    }
+    return JHN_OK;
+}
+
+void tc_destroy(jhn_v2v *net)
+{
+    if (!net->tc) return;
+    if (net->tc->blob) cudaFree(net->tc->blob);
+    delete net->tc;
+    net->tc = nullptr;
+}
+
+// ---- buffers of one forward ------------------------------------------------------------------
+struct TcBuffers {
+    uint4 *vol_ps;                 // PS input volume        [B][8][C1/8][h+2][(h+2)^2]
+    uint4 *A, *Bq, *C, *Dd, *E;    // h-grid BP tensors      [B][C2/8][h+2][(h+2)^2]
+    uint4 *Xps;                    // PS copy of front1 out  [B][8][C2/8][q+2][(q+2)^2]
+    uint4 *Pq, *Q, *R;             // q-grid BP tensors      [B][C4/8][q+2][(q+2)^2]
+    float *stats;                  // [11][B][96][2]
+};
+
+static size_t bp_units(int B, int cpad, int D) { return (size_t)B * (cpad / 8) * (D + 2) * (D + 2) * (D + 2); }
+
+static void carve(Arena &a, const jhn_v2v *net, int B, int G, TcBuffers &t, bool with_vol)
+{
+    const TcNet *tc = net->tc;
+    const int h = G / 2, q = G / 4;
+    const int c1 = tc->layer[L_FRONT0].cin_pad, c2 = tc->layer[L_FRONT0].cout_pad, c4 = tc->layer[L_POOL].cout_pad;
+    t.vol_ps = with_vol ? a.take<uint4>(8 * bp_units(B, c1, h)) : nullptr;
+    t.A = a.take<uint4>(bp_units(B, c2, h)); t.Bq = a.take<uint4>(bp_units(B, c2, h)); t.C = a.take<uint4>(bp_units(B, c2, h));
+    t.Dd = a.take<uint4>(bp_units(B, c2, h)); t.E = a.take<uint4>(bp_units(B, c2, h));
+    t.Xps = a.take<uint4>(8 * bp_units(B, c2, q));
+    t.Pq = a.take<uint4>(bp_units(B, c4, q)); t.Q = a.take<uint4>(bp_units(B, c4, q)); t.R = a.take<uint4>(bp_units(B, c4, q));
+    t.stats = a.take<float>((size_t)11 * B * 96 * 2);
+}
+
+size_t tc_volume_bytes(const jhn_v2v *net, int B, int G)
+{
+    return 8 * bp_units(B, net->tc->layer[L_FRONT0].cin_pad, G / 2) * 16;
+}
+
+size_t tc_workspace(const jhn_v2v *net, int B, int G)
+{
+    Arena a(nullptr, 0);
+    TcBuffers t;
+    carve(a, net, B, G, t, true);
+    return a.off;
+}
+
+namespace {
+struct TcCtx {
+    const jhn_v2v *net; int B; cudaStream_t st; int sms;
+
+    int make_map(CUtensorMap *m, const void *base, int chunks_total, int D, int KC, int PB) const
+    {
+        const int Wp = D + 2;
+        cuuint64_t dims[4] = {8, (cuuint64_t)Wp * Wp, (cuuint64_t)Wp, (cuuint64_t)chunks_total};
+        cuuint64_t strides[3] = {16, (cuuint64_t)Wp * Wp * 16, (cuuint64_t)Wp * Wp * Wp * 16};
+        cuuint32_t box[4] = {8, (cuuint32_t)PB, 1, (cuuint32_t)KC};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(JHN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) D=%d KC=%d PB=%d", (int)r, D, KC, PB);
+        return JHN_OK;
+    }
+
+    // in: BP or PS tensor with `chunks_in` chunks per sample on grid side D (the GEMM-row grid)
+    int conv(int l, const uint4 *in, int chunks_in, int D, void *out, int chunks_out, float *stats) const
+    {
+        const TcLayer &T = net->tc->layer[l];
+        TcProgram P;
+        JHN_TRY(build_program(P, kLayerKind[l], T.cin_pad, T.cout_pad, D, net->tc->max_smem));
+        CUtensorMap map;
+        JHN_TRY(make_map(&map, in, B * chunks_in, D, P.KC, P.PB));
+        TcLaunch L;
+        L.w = T.w; L.bias = T.bias; L.out = out; L.stats = stats; L.B = B; L.D = D; L.CJ_in = chunks_in; L.CJ_out = chunks_out;
+        L.NT = tiles_per_plane(D); L.total_tiles = B * D * L.NT * P.tile_taps; L.Kout = T.cout;
+        const int grid = L.total_tiles < sms ? L.total_tiles : sms;
+        const char *name = kLayerKind[l] == 0 ? (P.resident ? "tc_conv_k3_resident" : "tc_conv_k3_streamed")
+                           : kLayerKind[l] == 1 ? "tc_conv_front_k3s2" : kLayerKind[l] == 2 ? "tc_conv_pool_k2s2"
+                           : kLayerKind[l] == 3 ? "tc_conv_up_convT" : "tc_conv_head_1x1";
+        JHN_LAUNCH(name, st, tc_conv_kernel<<<grid, TC_THREADS, program_smem(P), st>>>(map, P, L));
+        return JHN_OK;
+    }
+    int norm(uint4 *x, const float *stats, int l, int D, const uint4 *residual, bool relu, const uint4 *post_add, uint4 *ps) const
+    {
+        const TcLayer &T = net->tc->layer[l];
+        const int nv = D * D * D, CJ = T.cout_pad / 8;
+        JHN_LAUNCH("tc_norm_act_kernel", st,
+                   tc_norm_act_kernel<<<dim3(cdiv(nv, 256), B * CJ), 256, 0, st>>>(x, stats, residual, post_add, ps, relu ? 1 : 0, D, CJ,
+                                                                                  T.cout_pad, 1.f / (float)nv, 1e-5f));
+        return JHN_OK;
+    }
+    int zero_border(uint4 *t, int chunks_total, int D) const { return tc_zero_border_launch(t, chunks_total, D, st); }
+};
+}  // namespace
+
+int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws, size_t ws_bytes,
+               cudaStream_t st)
+{
+    const TcNet *tc = net->tc;
+    if (!tc) return fail(JHN_ERR_ARG, "network was not created with JHN_BF16");
+    const int h = G / 2, q = G / 4;
+    if (h + 2 > 63) return fail(JHN_ERR_SHAPE, "bf16 path supports grid sides up to 122 (TMA box limit); got %d", G);
+    Arena a(ws, ws_bytes);
+    TcBuffers t;
+    carve(a, net, B, G, t, in_layout != JHN_VOL_V2V_BF16);
+    if (!a.ok()) return fail(JHN_ERR_WORKSPACE, "v2v bf16 workspace: need %zu bytes, got %zu", a.off, ws_bytes);
+    int dev = 0, sms = 0;
+    JHN_CUDA(cudaGetDevice(&dev));
+    JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TcCtx c{net, B, st, sms};
+    const int j1 = tc->layer[L_FRONT0].cin_pad / 8, j2 = tc->layer[L_FRONT0].cout_pad / 8, j4 = tc->layer[L_POOL].cout_pad / 8;
+    const uint4 *vol = (const uint4 *)volume_in;
+    if (in_layout != JHN_VOL_V2V_BF16) {
+        JHN_TRY(c.zero_border(t.vol_ps, B * 8 * j1, h));
+        const size_t nv = (size_t)G * G * G;
+        JHN_LAUNCH("tc_ncdhw_to_ps_kernel", st,
+                   tc_ncdhw_to_ps_kernel<<<dim3(cdiv(nv, 256), B * j1), 256, 0, st>>>((const float *)volume_in, t.vol_ps, net->K, G, j1));
+        vol = t.vol_ps;
+    }
+    JHN_CUDA(cudaMemsetAsync(t.stats, 0, (size_t)11 * B * 96 * 2 * sizeof(float), st));
+    uint4 *hb[5] = {t.A, t.Bq, t.C, t.Dd, t.E};
+    for (int i = 0; i < 5; ++i) JHN_TRY(c.zero_border(hb[i], B * j2, h));
+    uint4 *qb[3] = {t.Pq, t.Q, t.R};
+    for (int i = 0; i < 3; ++i) JHN_TRY(c.zero_border(qb[i], B * j4, q));
+    JHN_TRY(c.zero_border(t.Xps, B * 8 * j2, q));
+    auto S = [&](int i) { return t.stats + (size_t)i * B * 96 * 2; };
+
+    JHN_TRY(c.conv(L_FRONT0, vol, 8 * j1, h, t.A, j2, S(0)));                         // front_layers.0   v2vnet.py:90
+    JHN_TRY(c.norm(t.A, S(0), L_FRONT0, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_FRONT1A, t.A, j2, h, t.Bq, j2, S(1)));                           // front_layers.1 (Res3DBlock)
+    JHN_TRY(c.norm(t.Bq, S(1), L_FRONT1A, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_FRONT1B, t.Bq, j2, h, t.C, j2, S(2)));
+    JHN_TRY(c.norm(t.C, S(2), L_FRONT1B, h, t.A, true, nullptr, t.Xps));              // x = C (+ PS copy for the pool)
+    JHN_TRY(c.conv(L_SKIPA, t.C, j2, h, t.A, j2, S(3)));                              // skip_res1        :76
+    JHN_TRY(c.norm(t.A, S(3), L_SKIPA, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_SKIPB, t.A, j2, h, t.Bq, j2, S(4)));
+    JHN_TRY(c.norm(t.Bq, S(4), L_SKIPB, h, t.C, true, nullptr, nullptr));             // s = Bq
+    JHN_TRY(c.conv(L_POOL, t.Xps, 8 * j2, q, t.Pq, j4, S(5)));                        // encoder_pool1    :77
+    JHN_TRY(c.norm(t.Pq, S(5), L_POOL, q, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_MIDA, t.Pq, j4, q, t.Q, j4, S(6)));                              // mid_res          :78
+    JHN_TRY(c.norm(t.Q, S(6), L_MIDA, q, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_MIDB, t.Q, j4, q, t.R, j4, S(7)));
+    JHN_TRY(c.norm(t.R, S(7), L_MIDB, q, t.Pq, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_UP, t.R, j4, q, t.A, j2, S(8)));                                 // decoder_upsample1 :79
+    JHN_TRY(c.norm(t.A, S(8), L_UP, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_DECA, t.A, j2, h, t.Dd, j2, S(9)));                              // decoder_res1     :80
+    JHN_TRY(c.norm(t.Dd, S(9), L_DECA, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_DECB, t.Dd, j2, h, t.E, j2, S(10)));
+    JHN_TRY(c.norm(t.E, S(10), L_DECB, h, t.A, true, t.Bq, nullptr));                 // relu(.. + x) + skip   :81
+    return c.conv(L_HEAD, t.E, j2, h, out, 0, nullptr);                               // output_layer     v2vnet.py:101
+}
+
+// Per-layer hook for the parity tests: fp32 NCDHW in -> (bf16 layout conversion) -> tensor-core conv ->
+// raw (bias added, not normalised) output as fp32 NCDHW.  `D` is the layer's OUTPUT grid side, except for
+// the transposed convolution where it is the INPUT grid side.
+int tc_debug_layer(const jhn_v2v *net, int l, const float *in, int B, int D, float *out, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    const TcNet *tc = net->tc;
+    if (!tc) return fail(JHN_ERR_ARG, "network was not created with JHN_BF16");
+    if (l < 0 || l >= NUM_LAYERS) return fail(JHN_ERR_ARG, "layer %d out of range", l);
+    const TcLayer &T = tc->layer[l];
+    const LayerDesc &d = net->desc[l];
+    const int kind = kLayerKind[l];
+    const int Din = (kind == 1 || kind == 2) ? 2 * D : D;        // input grid side
+    const int Dout = kind == 3 ? 2 * D : D;
+    const int ji = T.cin_pad / 8, jo = T.cout_pad / 8;
+    Arena a(ws, ws_bytes);
+    const bool ps = kind == 1 || kind == 2;
+    uint4 *tin = a.take<uint4>(ps ? 8 * bp_units(B, T.cin_pad, D) : bp_units(B, T.cin_pad, D));
+    uint4 *tout = a.take<uint4>(bp_units(B, T.cout_pad, Dout));
+    float *stats = a.take<float>((size_t)B * 96 * 2);
+    if (!a.ok()) return fail(JHN_ERR_WORKSPACE, "debug layer workspace: need %zu bytes, got %zu", a.off, ws_bytes);
+    int dev = 0, sms = 0;
+    JHN_CUDA(cudaGetDevice(&dev));
+    JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TcCtx c{net, B, st, sms};
+    JHN_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 96 * 2 * sizeof(float), st));
+    JHN_TRY(c.zero_border(tin, B * (ps ? 8 : 1) * ji, D));
+    if (ps) {
+        const size_t nv = (size_t)Din * Din * Din;
+        JHN_LAUNCH("tc_ncdhw_to_ps_kernel", st, tc_ncdhw_to_ps_kernel<<<dim3(cdiv(nv, 256), B * ji), 256, 0, st>>>(in, tin, d.cin, Din, ji));
+    } else {
+        const int nv = D * D * D;
+        JHN_LAUNCH("tc_ncdhw_to_bp_kernel", st, tc_ncdhw_to_bp_kernel<<<dim3(cdiv(nv, 256), B * ji), 256, 0, st>>>(in, tin, d.cin, D, ji));
+    }
+    if (kind == 4) return c.conv(l, tin, ji, D, out, 0, nullptr);
+    JHN_TRY(c.zero_border(tout, B * jo, Dout));
+    JHN_TRY(c.conv(l, tin, (ps ? 8 : 1) * ji, D, tout, jo, stats));
+    const int nvo = Dout * Dout * Dout;
+    JHN_LAUNCH("tc_bp_to_ncdhw_kernel", st, tc_bp_to_ncdhw_kernel<<<dim3(cdiv(nvo, 256), B * jo), 256, 0, st>>>(tout, out, d.cout, Dout, jo));
+    return JHN_OK;
+}
+
+size_t tc_debug_workspace(const jhn_v2v *net, int l, int B, int D)
+{
+    const TcLayer &T = net->tc->layer[l];
+    const int kind = kLayerKind[l];
+    const int Dout = kind == 3 ? 2 * D : D;
+    Arena a(nullptr, 0);
+    const bool ps = kind == 1 || kind == 2;
+    a.take<uint4>(ps ? 8 * bp_units(B, T.cin_pad, D) : bp_units(B, T.cin_pad, D));
+    a.take<uint4>(bp_units(B, T.cout_pad, Dout));
+    a.take<float>((size_t)B * 96 * 2);
+    return a.off;
+}
+
 }  // namespace jhn

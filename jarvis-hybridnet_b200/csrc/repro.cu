@@ -222,9 +222,6 @@ template <> struct Vec<__nv_bfloat16> {
     }
 };
 
-// layout of the bf16 volume consumed by the tensor-core front convolution (conv_tc.cu)
-__device__ __forceinline__ size_t v2v_in_offset(int b, int I, int J, int Kz, int chunk, int h);
-
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(256)
 gather_mean_kernel(const T *__restrict__ hm, const int32_t *__restrict__ idx, int ncam, int K, int hs, int G,
@@ -244,12 +241,40 @@ gather_mean_kernel(const T *__restrict__ hm, const int32_t *__restrict__ idx, in
         Vec<T>::add(base + ((size_t)c * hs * hs + flat) * KP, acc);
     }
     const float fn = (float)ncam;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        float m = __fdiv_rn(acc[k], fn);                            // torch.mean        :103-105
+        if (post_divide != 1.f) m = __fdiv_rn(m, post_divide);      // heatmaps3D/255.   model.py:72
+        acc[k] = m;
+    }
     if (LAYOUT == JHN_VOL_NCDHW_F32) {
         float *out = (float *)out_ + (size_t)b * K * nv + v;
-        for (int k = 0; k < K; ++k) {
-            float m = __fdiv_rn(acc[k], fn);                        // torch.mean        :103-105
-            if (post_divide != 1.f) m = __fdiv_rn(m, post_divide);  // heatmaps3D/255.   model.py:72
-            out[(size_t)k * nv] = m;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) out[(size_t)k * nv] = acc[k];
+    } else {
+        // parity-split, channel-blocked bf16 volume read by the tensor-core front convolution (conv_tc.cu):
+        // [b][s = (I&1,J&1,Kz&1)][j][zp][pp][8] on the G/2 grid; channel chunks beyond K are written as zeros
+        const int I = (int)(v / ((size_t)G * G)), r = (int)(v - (size_t)I * G * G), J = r / G, Kz = r - J * G;
+        const int CJ = (K + 15) / 16 * 2, Wh = G / 2 + 2;
+        const int s = ((I & 1) * 2 + (J & 1)) * 2 + (Kz & 1);
+        uint4 *out = (uint4 *)out_;
+        const size_t pos = ((size_t)(I >> 1) + 1) * Wh * Wh + (size_t)((J >> 1) + 1) * Wh + (Kz >> 1) + 1;
+        const size_t chunk_stride = (size_t)Wh * Wh * Wh;
+        const size_t base = (((size_t)b * 8 + s) * CJ) * chunk_stride + pos;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < CJ) {
+                uint32_t pk[4] = {0, 0, 0, 0};
+                if (j < KP / 8) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * j + 2 * i], acc[8 * j + 2 * i + 1]);
+                        pk[i] = *reinterpret_cast<uint32_t *>(&h2);
+                    }
+                }
+                out[base + (size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
         }
     }
 }
@@ -277,7 +302,12 @@ static int run_gather(const ReprojectArgs &a, const T *hm_cl, const int32_t *idx
                                                                                   a.post_divide, a.volume_out)));
         return JHN_OK;
     }
-    return fail(JHN_ERR_ARG, "volume layout %d not supported by this build", a.layout);
+    const int CJ = (a.K + 15) / 16 * 2;
+    JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
+    JHN_LAUNCH("gather_mean_kernel", st,
+               (gather_mean_kernel<T, JHN_VOL_V2V_BF16><<<grid, 256, 0, st>>>(hm_cl, idx, a.ncam, a.K, a.hs, a.G,
+                                                                             a.post_divide, a.volume_out)));
+    return JHN_OK;
 }
 
 int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStream_t st)

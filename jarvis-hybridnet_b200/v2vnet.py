@@ -79,6 +79,25 @@ class V2VNet(nn.Module):
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
         return self._ws
 
+    def debug_layer(self, layer, x, D):
+        """Test aid: run convolution `layer` (index into V2V_LAYERS) alone on the tensor-core path.
+        x: fp32 NCDHW input of that layer; D: output grid side (input side for the transposed conv).
+        Returns the raw fp32 NCDHW output (bias added, no InstanceNorm)."""
+        _lib.require_cuda(x)
+        lib = _lib.load()
+        h = self._get_handle()
+        name, kind, cim, com, k = V2V_LAYERS[layer]
+        B = x.shape[0]
+        Dout = 2 * D if kind == "convT" else D
+        need = _lib.c_size_t()
+        _lib.check(lib.jhn_v2v_debug_layer_workspace_bytes(h, layer, B, D, need))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+        out = torch.zeros((B, com * self.K, Dout, Dout, Dout), dtype=torch.float32, device=x.device)
+        xin = x.contiguous().float()
+        _lib.check(lib.jhn_v2v_debug_layer(h, layer, _lib.dptr(xin), B, D, _lib.dptr(out), _lib.dptr(ws), ws.numel(),
+                                           _lib.stream_ptr()))
+        return out
+
     def forward(self, x):
         """x [B,K,G,G,G] fp32 (already /255, model.py:72) -> [B,K,G/2,G/2,G/2] fp32."""
         _lib.require_cuda(x)
