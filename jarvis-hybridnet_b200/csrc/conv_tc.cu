@@ -6,8 +6,8 @@
 //     act[b][j][zp][pp][8]   bf16,  j = channel/8,  zp in [0,D+2),  pp = yp*(D+2)+xp in [0,(D+2)^2)
 // i.e. for each 8-channel chunk the zero-padded volume is a flat array of 16-byte voxels.  A GEMM row
 // block is 128 consecutive padded positions of one z-plane; the input window of tap (dz,dy,dx) is the
-// same flat array shifted by dy*(D+2)+dx positions in plane z+dz.  A TMA box [KC chunks][PB positions]
-// (PB = 128 + halo) lands in smem as [chunk][position][8] which IS the canonical no-swizzle K-major UMMA
+// same flat array shifted by dy*(D+2)+dx positions in plane z+dz.  A box [KC chunks][PB positions]
+// (PB = 128 + halo; one contiguous TMA bulk copy per chunk) lands in smem as [chunk][position][8] which IS the canonical no-swizzle K-major UMMA
 // operand layout (8 rows x 16 B core matrices, SBO = 128 B between row groups, LBO = PB*16 B between the
 // two K-chunks of one K=16 MMA) for any start row -> the 9 in-plane taps are 9 descriptors into one tile,
 // and the tile is fetched from L2 once per plane instead of once per tap.  Pad positions produce garbage
@@ -17,16 +17,16 @@
 // epilogue scatters to the 8 output parities.
 //
 // Kernel: persistent, warp-specialised, one CTA per SM.
-//     warp 0     TMA producer (one elected lane): activation boxes (+ weight slabs when not resident)
-//     warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M=128, N=Cout_pad, K=16
+//     warp 0     TMA producer (one elected lane): cp.async.bulk of activation boxes (+ weight slabs when
+//                not resident) into a ring of shared-memory slots, completion on mbarriers
+//     warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M=128, N=Cout_pad, K=16,
+//                descriptors formed from a per-tile offset list precomputed in shared memory
 //     warps 2-5  epilogue: tcgen05.ld -> bias -> pad mask -> bf16 store (coalesced 512 B per chunk) and
 //                per-channel sum / sum-of-squares for the following InstanceNorm (fused statistics)
 // Weights of the C->C 3x3x3 layers (124 KB bf16) stay resident in shared memory for the CTA's lifetime.
 // The work of a layer is a "stage program" (TcProgram) built on the host: per tile a list of TMA boxes and,
 // per box, the taps (smem row offset, weight index) to issue against it.
-#include <cuda.h>
-
-#include <vector>
+#include <cstring>
 
 #include "v2v.cuh"
 
@@ -54,6 +54,7 @@ struct TcProgram {
 };
 
 struct TcLaunch {
+    const void *in;                                   // BP / PS bf16 input tensor
     const __nv_bfloat16 *w;                           // [tap][KC][NOUT][8] bf16
     const float *bias;                                // [NOUT] fp32 (zero padded)
     void *out;                                        // BP bf16 (RAW/CONVT) or NCDHW fp32 (HEAD)
@@ -94,11 +95,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "{\n.reg .pred P1;\nLAB_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
         "@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -143,6 +139,8 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int N)
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 192;
 constexpr int EPI_TILE_FLOATS = 32 * 17;
+constexpr int MAX_MMAS = 192;                         // per tile: 9 stages x 3 taps x 6 k-steps at most
+constexpr int TC_SMEM_TAIL = 4 * EPI_TILE_FLOATS * 4 + 128 * 4 + 30 * 8 + MAX_MMAS * 8 + 1024;
 
 struct TileCoord { int b, z, pt, tap; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const TcLaunch &L, int tile_taps)
@@ -156,7 +154,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const TcLaunch &L, int t
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcProgram P, const TcLaunch L)
+tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,6 +169,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 128);
     uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *wbar = bars + 20;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
+    int *stage_first = reinterpret_cast<int *>(bars + 22);            // [MAX_STAGES + 1]
+    uint2 *mma_list = reinterpret_cast<uint2 *>(bars + 30);           // [MAX_MMAS] (a_off16, b_off16)
 
     // contiguous tile range of this CTA
     const int t_begin = (int)((long long)L.total_tiles * blockIdx.x / gridDim.x);
@@ -212,10 +212,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                     mbar_wait(smem_u32(empty + slot), phase ^ 1);
                     const uint32_t fb = smem_u32(full + slot);
                     uint8_t *dst = ring + (size_t)slot * P.stage_bytes;
-                    uint32_t bytes = (uint32_t)(P.KC * P.PB * 16);
+                    // one contiguous run of positions per channel chunk; clipped at the end of the plane (the
+                    // rows left stale only feed pad outputs, which the epilogue overwrites with zeros)
+                    const int start = p0 + S.pos_off;
+                    const int npos = min(P.PB, PP - start);
+                    const uint32_t run = (uint32_t)npos * 16;
+                    uint32_t bytes = run * (uint32_t)P.KC;
                     if (!P.resident) bytes += (uint32_t)(S.ntaps * tap_bytes);
                     mbar_expect_tx(fb, bytes);
-                    tma_load_4d(smem_u32(dst), &tmap, fb, 0, p0 + S.pos_off, c.z + S.dz, c.b * L.CJ_in + S.chunk0);
+                    const size_t unit0 = ((size_t)(c.b * L.CJ_in + S.chunk0) * Wp + (c.z + S.dz)) * PP + start;
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(L.in) + unit0 * 16;
+                    const size_t chunk_stride = (size_t)Wp * PP * 16;
+                    for (int j = 0; j < P.KC; ++j)
+                        bulk_load(smem_u32(dst + (size_t)j * P.PB * 16), src + j * chunk_stride, run, fb);
                     if (!P.resident)
                         bulk_load(smem_u32(dst + P.stage_bytes_a),
                                   reinterpret_cast<const uint8_t *>(L.w) + (size_t)S.wtap0 * tap_bytes,
@@ -228,31 +237,46 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         // =================================== MMA issuer ======================================
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(P.NOUT);
-            const uint32_t lbo_a = (uint32_t)P.PB * 16, lbo_b = (uint32_t)P.NOUT * 16;
+            const uint32_t lbo_a = (uint32_t)P.PB, lbo_b = (uint32_t)P.NOUT;       // in 16-byte units
+            const uint32_t tap_units = (uint32_t)tap_bytes >> 4;
+            // flatten the stage program into one (A offset, B offset) pair per MMA, in descriptor units
+            int n = 0;
+            for (int s = 0; s < P.nstages; ++s) {
+                const TcStage &S = P.st[s];
+                stage_first[s] = n;
+                for (int k = 0; k < S.ntaps; ++k) {
+                    const uint32_t wsel = P.tile_taps > 1 ? 0u : (P.resident ? (uint32_t)S.taps[k].widx : (uint32_t)k);
+                    for (int kc = 0; kc < P.KC; kc += 2)
+                        mma_list[n++] = make_uint2((uint32_t)S.taps[k].aoff + kc * lbo_a, wsel * tap_units + kc * lbo_b);
+                }
+            }
+            stage_first[P.nstages] = n;
+            // descriptor words: lo = start address (16-B units) | LBO << 16, hi = SBO (=8 units) | version 1
+            const uint32_t a_lo_c = lbo_a << 16, b_lo_c = lbo_b << 16, hi_c = 8u | (1u << 14);
+            const uint32_t w_units = smem_u32(w_smem) >> 4, ring_units = smem_u32(ring) >> 4;
+            const uint32_t slot_units = (uint32_t)P.stage_bytes >> 4, a_units = (uint32_t)P.stage_bytes_a >> 4;
             if (P.resident) mbar_wait(smem_u32(wbar), 0);
             int slot = 0; uint32_t phase = 0;
             int ab = 0; uint32_t aphase = 0;
             for (int t = t_begin; t < t_end; ++t) {
-                const TileCoord c = decode_tile(t, L, P.tile_taps);
+                const uint32_t tile_tap = P.tile_taps > 1 ? (uint32_t)(t % P.tile_taps) : 0u;
                 mbar_wait(smem_u32(tempty + ab), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(ab * P.NOUT);
                 uint32_t acc = 0;
                 for (int s = 0; s < P.nstages; ++s) {
-                    const TcStage &S = P.st[s];
                     mbar_wait(smem_u32(full + slot), phase);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(ring + (size_t)slot * P.stage_bytes);
-                    for (int k = 0; k < S.ntaps; ++k) {
-                        const uint32_t a_tap = a0 + (uint32_t)S.taps[k].aoff * 16;
-                        const int widx = P.tile_taps > 1 ? c.tap : S.taps[k].widx;
-                        const uint32_t b_tap = P.resident ? smem_u32(w_smem) + (uint32_t)(widx * tap_bytes)
-                                                          : a0 + (uint32_t)P.stage_bytes_a + (uint32_t)(k * tap_bytes);
-                        for (int kc = 0; kc < P.KC; kc += 2) {
-                            tc_mma_bf16(d_tmem, umma_desc(a_tap + kc * lbo_a, lbo_a, 128),
-                                        umma_desc(b_tap + kc * lbo_b, lbo_b, 128), idesc, acc);
-                            acc = 1;
-                        }
+                    const uint32_t a0 = ring_units + (uint32_t)slot * slot_units;
+                    const uint32_t b0 = P.resident ? w_units + tile_tap * tap_units : a0 + a_units;
+                    const int e1 = stage_first[s + 1];
+#pragma unroll 3
+                    for (int e = stage_first[s]; e < e1; ++e) {
+                        const uint2 o = mma_list[e];
+                        const uint64_t adesc = ((uint64_t)hi_c << 32) | (uint64_t)(a_lo_c | (a0 + o.x));
+                        const uint64_t bdesc = ((uint64_t)hi_c << 32) | (uint64_t)(b_lo_c | (b0 + o.y));
+                        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, acc);
+                        acc = 1;
                     }
                     tc_commit(smem_u32(empty + slot));               // frees the smem slot when the MMAs retire
                     if (++slot == P.nslots) { slot = 0; phase ^= 1; }
@@ -525,23 +549,6 @@ tc_ncdhw_to_bp_kernel(const float *__restrict__ in, uint4 *__restrict__ out, int
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 static inline int tiles_per_plane(int D) { return cdiv((long long)(D - 1) * (D + 2) + D, TILE_M); }
 
@@ -581,7 +588,7 @@ static int build_program(TcProgram &P, int kind, int cin_pad, int cout_pad, int 
     };
     if (kind == 0) {
         P.ntaps_total = 27;
-        const bool resident = (size_t)27 * tap_bytes + 4 * ((size_t)P.KC * (TILE_M + 2 * Wp + 2) * 16) + 16384 <= (size_t)max_smem;
+        const bool resident = (size_t)27 * tap_bytes + 3 * ((size_t)P.KC * (TILE_M + 2 * Wp + 2) * 16) + TC_SMEM_TAIL <= (size_t)max_smem;
         P.resident = resident ? 1 : 0;
         if (resident) {                       // one box per z-plane, 9 in-plane taps each
             P.PB = TILE_M + 2 * Wp + 2;
@@ -629,7 +636,7 @@ static int build_program(TcProgram &P, int kind, int cin_pad, int cout_pad, int 
     P.stage_bytes_a = (int)align_up((size_t)P.KC * P.PB * 16, 128);
     P.stage_bytes = P.stage_bytes_a + (P.resident ? 0 : (int)align_up((size_t)max_taps * tap_bytes, 128));
     P.w_bytes = P.resident ? (int)align_up((size_t)P.ntaps_total * tap_bytes, 128) : 0;
-    const int fixed = P.w_bytes + 4 * EPI_TILE_FLOATS * 4 + 128 * 4 + 256 + 1024;
+    const int fixed = P.w_bytes + TC_SMEM_TAIL;
     int slots = (max_smem - fixed) / P.stage_bytes;
     if (slots > 8) slots = 8;
     if (slots < 2) return fail(JHN_ERR_SHAPE, "tensor-core conv: tile does not fit shared memory (grid side %d)", D);
@@ -639,14 +646,13 @@ static int build_program(TcProgram &P, int kind, int cin_pad, int cout_pad, int 
 
 static size_t program_smem(const TcProgram &P)
 {
-    return (size_t)P.w_bytes + (size_t)P.nslots * P.stage_bytes + 4 * EPI_TILE_FLOATS * 4 + 128 * 4 + 256 + 1024;
+    return (size_t)P.w_bytes + (size_t)P.nslots * P.stage_bytes + TC_SMEM_TAIL;
 }
 
 static const int kLayerKind[NUM_LAYERS] = {1, 0, 0, 2, 0, 0, 3, 0, 0, 0, 0, 4};
 
 int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st)
 {
-    if (!encode_fn()) return fail(JHN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     int dev = 0, max_smem = 0;
     JHN_CUDA(cudaGetDevice(&dev));
     JHN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -729,36 +735,20 @@ namespace {
 struct TcCtx {
     const jhn_v2v *net; int B; cudaStream_t st; int sms;
 
-    int make_map(CUtensorMap *m, const void *base, int chunks_total, int D, int KC, int PB) const
-    {
-        const int Wp = D + 2;
-        cuuint64_t dims[4] = {8, (cuuint64_t)Wp * Wp, (cuuint64_t)Wp, (cuuint64_t)chunks_total};
-        cuuint64_t strides[3] = {16, (cuuint64_t)Wp * Wp * 16, (cuuint64_t)Wp * Wp * Wp * 16};
-        cuuint32_t box[4] = {8, (cuuint32_t)PB, 1, (cuuint32_t)KC};
-        cuuint32_t es[4] = {1, 1, 1, 1};
-        CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, es,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(JHN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) D=%d KC=%d PB=%d", (int)r, D, KC, PB);
-        return JHN_OK;
-    }
-
     // in: BP or PS tensor with `chunks_in` chunks per sample on grid side D (the GEMM-row grid)
     int conv(int l, const uint4 *in, int chunks_in, int D, void *out, int chunks_out, float *stats) const
     {
         const TcLayer &T = net->tc->layer[l];
         TcProgram P;
         JHN_TRY(build_program(P, kLayerKind[l], T.cin_pad, T.cout_pad, D, net->tc->max_smem));
-        CUtensorMap map;
-        JHN_TRY(make_map(&map, in, B * chunks_in, D, P.KC, P.PB));
         TcLaunch L;
-        L.w = T.w; L.bias = T.bias; L.out = out; L.stats = stats; L.B = B; L.D = D; L.CJ_in = chunks_in; L.CJ_out = chunks_out;
+        L.in = in; L.w = T.w; L.bias = T.bias; L.out = out; L.stats = stats; L.B = B; L.D = D; L.CJ_in = chunks_in; L.CJ_out = chunks_out;
         L.NT = tiles_per_plane(D); L.total_tiles = B * D * L.NT * P.tile_taps; L.Kout = T.cout;
         const int grid = L.total_tiles < sms ? L.total_tiles : sms;
         const char *name = kLayerKind[l] == 0 ? (P.resident ? "tc_conv_k3_resident" : "tc_conv_k3_streamed")
                            : kLayerKind[l] == 1 ? "tc_conv_front_k3s2" : kLayerKind[l] == 2 ? "tc_conv_pool_k2s2"
                            : kLayerKind[l] == 3 ? "tc_conv_up_convT" : "tc_conv_head_1x1";
-        JHN_LAUNCH(name, st, tc_conv_kernel<<<grid, TC_THREADS, program_smem(P), st>>>(map, P, L));
+        JHN_LAUNCH(name, st, tc_conv_kernel<<<grid, TC_THREADS, program_smem(P), st>>>(P, L));
         return JHN_OK;
     }
     int norm(uint4 *x, const float *stats, int l, int D, const uint4 *residual, bool relu, const uint4 *post_add, uint4 *ps) const
@@ -780,7 +770,7 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
     const TcNet *tc = net->tc;
     if (!tc) return fail(JHN_ERR_ARG, "network was not created with JHN_BF16");
     const int h = G / 2, q = G / 4;
-    if (h + 2 > 63) return fail(JHN_ERR_SHAPE, "bf16 path supports grid sides up to 122 (TMA box limit); got %d", G);
+    if (h + 2 > 63) return fail(JHN_ERR_SHAPE, "bf16 path supports grid sides up to 122; got %d", G);
     Arena a(ws, ws_bytes);
     TcBuffers t;
     carve(a, net, B, G, t, in_layout != JHN_VOL_V2V_BF16);
