@@ -139,8 +139,8 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int N)
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 192;
 constexpr int EPI_TILE_FLOATS = 32 * 17;
-constexpr int MAX_MMAS = 192;                         // per tile: 9 stages x 3 taps x 6 k-steps at most
-constexpr int TC_SMEM_TAIL = 4 * EPI_TILE_FLOATS * 4 + 128 * 4 + 30 * 8 + MAX_MMAS * 8 + 1024;
+constexpr int MAX_DESC = 768;                         // descriptor pairs: (MMAs per tile) x (ring slots)
+constexpr int TC_SMEM_TAIL = 4 * EPI_TILE_FLOATS * 4 + 128 * 4 + 30 * 8 + MAX_DESC * 8 + 1024;
 
 struct TileCoord { int b, z, pt, tap; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const TcLaunch &L, int tile_taps)
@@ -170,13 +170,18 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
     uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *wbar = bars + 20;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
     int *stage_first = reinterpret_cast<int *>(bars + 22);            // [MAX_STAGES + 1]
-    uint2 *mma_list = reinterpret_cast<uint2 *>(bars + 30);           // [MAX_MMAS] (a_off16, b_off16)
+    uint2 *desc_list = reinterpret_cast<uint2 *>(bars + 30);          // [nslots][MMAs per tile] (A desc lo, B desc lo)
 
     // contiguous tile range of this CTA
     const int t_begin = (int)((long long)L.total_tiles * blockIdx.x / gridDim.x);
     const int t_end = (int)((long long)L.total_tiles * (blockIdx.x + 1) / gridDim.x);
-    const uint32_t tmem_cols = (2 * P.NOUT <= 32) ? 32 : (2 * P.NOUT <= 64) ? 64 : (2 * P.NOUT <= 128) ? 128 : 256;
+    // TMEM: 2 tile buffers x 2 interleaved accumulators (the K loop of a tile alternates between two
+    // independent accumulation chains; the epilogue adds them) x NOUT fp32 columns
+    const uint32_t tmem_need = 4u * (uint32_t)P.NOUT;
+    const uint32_t tmem_cols = tmem_need <= 32 ? 32 : tmem_need <= 64 ? 64 : tmem_need <= 128 ? 128 : tmem_need <= 256 ? 256 : 512;
 
+    bool dual = true;                                 // second accumulator is written in every stage?
+    for (int s = 0; s < P.nstages; ++s) dual = dual && (P.st[s].ntaps * (P.KC / 2) >= 2);
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.nslots; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
@@ -235,48 +240,68 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
         }
     } else if (warp == 1) {
         // =================================== MMA issuer ======================================
-        if (elect_one()) {
-            const uint32_t idesc = umma_idesc_bf16(P.NOUT);
-            const uint32_t lbo_a = (uint32_t)P.PB, lbo_b = (uint32_t)P.NOUT;       // in 16-byte units
-            const uint32_t tap_units = (uint32_t)tap_bytes >> 4;
-            // flatten the stage program into one (A offset, B offset) pair per MMA, in descriptor units
-            int n = 0;
-            for (int s = 0; s < P.nstages; ++s) {
-                const TcStage &S = P.st[s];
-                stage_first[s] = n;
-                for (int k = 0; k < S.ntaps; ++k) {
-                    const uint32_t wsel = P.tile_taps > 1 ? 0u : (P.resident ? (uint32_t)S.taps[k].widx : (uint32_t)k);
-                    for (int kc = 0; kc < P.KC; kc += 2)
-                        mma_list[n++] = make_uint2((uint32_t)S.taps[k].aoff + kc * lbo_a, wsel * tap_units + kc * lbo_b);
-                }
-            }
-            stage_first[P.nstages] = n;
-            // descriptor words: lo = start address (16-B units) | LBO << 16, hi = SBO (=8 units) | version 1
-            const uint32_t a_lo_c = lbo_a << 16, b_lo_c = lbo_b << 16, hi_c = 8u | (1u << 14);
+        // Flatten the stage program into complete descriptor low words, one (A, B) pair per MMA and ring slot,
+        // so that the issue loop is LDS.64 -> 2x R2UR -> UTCHMMA.  Descriptor words: lo = start address
+        // (16-byte units) | LBO << 16, hi = SBO (= 8 units, 128 B) | version 1.
+        const uint32_t lbo_a = (uint32_t)P.PB, lbo_b = (uint32_t)P.NOUT;           // in 16-byte units
+        const uint32_t tap_units = (uint32_t)tap_bytes >> 4;
+        int n_mma = 0;
+        for (int s = 0; s < P.nstages; ++s) {
+            if (lane == 0) stage_first[s] = n_mma;
+            n_mma += P.st[s].ntaps * (P.KC / 2);
+        }
+        if (lane == 0) stage_first[P.nstages] = n_mma;
+        {
+            const uint32_t a_lo_c = lbo_a << 16, b_lo_c = lbo_b << 16;
             const uint32_t w_units = smem_u32(w_smem) >> 4, ring_units = smem_u32(ring) >> 4;
             const uint32_t slot_units = (uint32_t)P.stage_bytes >> 4, a_units = (uint32_t)P.stage_bytes_a >> 4;
+            const int kpt = P.KC / 2;
+            for (int i = lane; i < n_mma * P.nslots; i += 32) {
+                const int slot = i / n_mma;
+                int e = i - slot * n_mma, s = 0;
+                while (e >= P.st[s].ntaps * kpt) { e -= P.st[s].ntaps * kpt; ++s; }
+                const int k = e / kpt, kc = 2 * (e - k * kpt);
+                const TcStage &S = P.st[s];
+                const uint32_t wsel = P.tile_taps > 1 ? 0u : (P.resident ? (uint32_t)S.taps[k].widx : (uint32_t)k);
+                const uint32_t a0 = ring_units + (uint32_t)slot * slot_units;
+                const uint32_t b0 = P.resident ? w_units : a0 + a_units;
+                desc_list[i] = make_uint2(a_lo_c | (a0 + (uint32_t)S.taps[k].aoff + kc * lbo_a),
+                                          b_lo_c | (b0 + wsel * tap_units + kc * lbo_b));
+            }
+        }
+        __syncwarp();
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_bf16(P.NOUT);
+            const uint64_t hi_c = (uint64_t)(8u | (1u << 14)) << 32;
+            const uint32_t nout = (uint32_t)P.NOUT;
             if (P.resident) mbar_wait(smem_u32(wbar), 0);
             int slot = 0; uint32_t phase = 0;
             int ab = 0; uint32_t aphase = 0;
             for (int t = t_begin; t < t_end; ++t) {
-                const uint32_t tile_tap = P.tile_taps > 1 ? (uint32_t)(t % P.tile_taps) : 0u;
+                const uint32_t tile_b = P.tile_taps > 1 ? (uint32_t)(t % P.tile_taps) * tap_units : 0u;
                 mbar_wait(smem_u32(tempty + ab), aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * P.NOUT);
-                uint32_t acc = 0;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * 2 * P.NOUT);
+                uint32_t acc0 = 0, acc1 = 0;
                 for (int s = 0; s < P.nstages; ++s) {
                     mbar_wait(smem_u32(full + slot), phase);
                     tc_fence_after();
-                    const uint32_t a0 = ring_units + (uint32_t)slot * slot_units;
-                    const uint32_t b0 = P.resident ? w_units + tile_tap * tap_units : a0 + a_units;
+                    const uint2 *dl = desc_list + slot * n_mma;
                     const int e1 = stage_first[s + 1];
-#pragma unroll 3
-                    for (int e = stage_first[s]; e < e1; ++e) {
-                        const uint2 o = mma_list[e];
-                        const uint64_t adesc = ((uint64_t)hi_c << 32) | (uint64_t)(a_lo_c | (a0 + o.x));
-                        const uint64_t bdesc = ((uint64_t)hi_c << 32) | (uint64_t)(b_lo_c | (b0 + o.y));
-                        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, acc);
-                        acc = 1;
+                    int e = stage_first[s];
+                    if (dual) {
+#pragma unroll 2
+                        for (; e + 1 < e1; e += 2) {
+                            const uint2 o0 = dl[e], o1 = dl[e + 1];
+                            tc_mma_bf16(d_tmem, hi_c | (uint64_t)o0.x, hi_c | (uint64_t)(o0.y + tile_b), idesc, acc0);
+                            tc_mma_bf16(d_tmem + nout, hi_c | (uint64_t)o1.x, hi_c | (uint64_t)(o1.y + tile_b), idesc, acc1);
+                            acc0 = 1; acc1 = 1;
+                        }
+                    }
+                    for (; e < e1; ++e) {
+                        const uint2 o = dl[e];
+                        tc_mma_bf16(d_tmem, hi_c | (uint64_t)o.x, hi_c | (uint64_t)(o.y + tile_b), idesc, acc0);
+                        acc0 = 1;
                     }
                     tc_commit(smem_u32(empty + slot));               // frees the smem slot when the MMAs retire
                     if (++slot == P.nslots) { slot = 0; phase ^= 1; }
@@ -315,10 +340,18 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
                 const int c0 = ci * 16;
                 if (c0 < P.NOUT) {
                     uint32_t r[16];
-                    tc_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ab * P.NOUT + c0), r);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ab * 2 * P.NOUT + c0);
+                    tc_ld16(taddr, r);
                     float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = valid ? __uint_as_float(r[i]) + bias_s[c0 + i] : 0.f;
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
+                    if (dual) {
+                        tc_ld16(taddr + (uint32_t)P.NOUT, r);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += __uint_as_float(r[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = valid ? v[i] : 0.f;
                     if (P.epi == EPI_HEAD) {
                         if (valid) {
                             float *o = reinterpret_cast<float *>(L.out);
@@ -421,6 +454,26 @@ tc_zero_border_kernel(uint4 *__restrict__ t, int D)
         for (int p = threadIdx.x; p < PP; p += blockDim.x) plane[p] = z4;
     } else {
         for (int p = threadIdx.x; p < Wp; p += blockDim.x) { plane[p] = z4; plane[(size_t)(Wp - 1) * Wp + p] = z4; }
+        for (int y = threadIdx.x; y < Wp; y += blockDim.x) { plane[(size_t)y * Wp] = z4; plane[(size_t)y * Wp + Wp - 1] = z4; }
+    }
+}
+
+// the same for up to 12 tensors in one launch (one block per z-plane of any of them)
+struct ZeroJobs { int n; int first[13]; int D[12]; uint4 *p[12]; };
+__global__ void __launch_bounds__(128)
+tc_zero_border_multi_kernel(const __grid_constant__ ZeroJobs J)
+{
+    int k = 0;
+    while (k + 1 < J.n && (int)blockIdx.x >= J.first[k + 1]) ++k;
+    const int D = J.D[k], Wp = D + 2, PP = Wp * Wp;
+    const int pl = blockIdx.x - J.first[k];                          // plane index over [chunks_total][Wp]
+    const int zp = pl % Wp;
+    uint4 *plane = J.p[k] + (size_t)pl * PP;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    if (zp == 0 || zp == Wp - 1) {
+        for (int q = threadIdx.x; q < PP; q += blockDim.x) plane[q] = z4;
+    } else {
+        for (int q = threadIdx.x; q < Wp; q += blockDim.x) { plane[q] = z4; plane[(size_t)(Wp - 1) * Wp + q] = z4; }
         for (int y = threadIdx.x; y < Wp; y += blockDim.x) { plane[(size_t)y * Wp] = z4; plane[(size_t)y * Wp + Wp - 1] = z4; }
     }
 }
@@ -639,6 +692,10 @@ static int build_program(TcProgram &P, int kind, int cin_pad, int cout_pad, int 
     const int fixed = P.w_bytes + TC_SMEM_TAIL;
     int slots = (max_smem - fixed) / P.stage_bytes;
     if (slots > 8) slots = 8;
+    int n_mma = 0;
+    for (int s = 0; s < P.nstages; ++s) n_mma += P.st[s].ntaps * (P.KC / 2);
+    while (slots > 2 && slots * n_mma > MAX_DESC) --slots;
+    if (slots * n_mma > MAX_DESC) return fail(JHN_ERR_SHAPE, "tensor-core conv: stage program too long (%d MMAs per tile)", n_mma);
     if (slots < 2) return fail(JHN_ERR_SHAPE, "tensor-core conv: tile does not fit shared memory (grid side %d)", D);
     P.nslots = slots;
     return JHN_OK;
@@ -789,11 +846,17 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
         vol = t.vol_ps;
     }
     JHN_CUDA(cudaMemsetAsync(t.stats, 0, (size_t)11 * B * 96 * 2 * sizeof(float), st));
-    uint4 *hb[5] = {t.A, t.Bq, t.C, t.Dd, t.E};
-    for (int i = 0; i < 5; ++i) JHN_TRY(c.zero_border(hb[i], B * j2, h));
-    uint4 *qb[3] = {t.Pq, t.Q, t.R};
-    for (int i = 0; i < 3; ++i) JHN_TRY(c.zero_border(qb[i], B * j4, q));
-    JHN_TRY(c.zero_border(t.Xps, B * 8 * j2, q));
+    {
+        ZeroJobs J;
+        uint4 *ptrs[9] = {t.A, t.Bq, t.C, t.Dd, t.E, t.Pq, t.Q, t.R, t.Xps};
+        const int chunks[9] = {B * j2, B * j2, B * j2, B * j2, B * j2, B * j4, B * j4, B * j4, B * 8 * j2};
+        const int sides[9] = {h, h, h, h, h, q, q, q, q};
+        J.n = 9;
+        int total = 0;
+        for (int i = 0; i < 9; ++i) { J.first[i] = total; J.D[i] = sides[i]; J.p[i] = ptrs[i]; total += chunks[i] * (sides[i] + 2); }
+        J.first[9] = total;
+        JHN_LAUNCH("tc_zero_border_kernel", st, tc_zero_border_multi_kernel<<<total, 128, 0, st>>>(J));
+    }
     auto S = [&](int i) { return t.stats + (size_t)i * B * 96 * 2; };
 
     JHN_TRY(c.conv(L_FRONT0, vol, 8 * j1, h, t.A, j2, S(0)));                         // front_layers.0   v2vnet.py:90

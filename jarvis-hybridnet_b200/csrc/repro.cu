@@ -5,16 +5,23 @@
 //   coarse_project_kernel  half-resolution grid -> per-camera distorted, clamped pixel coordinates
 //                          (repro_layer.py:46-68).  Separately rounded fp32 ops in the reference's order;
 //                          the K=4 dot product is cuBLAS/MKL's FMA chain.
-//   fine_index_kernel      ATen upsample_trilinear3d (align_corners=False, scale 1/2) of both coordinate
-//                          volumes, /2, truncate, y*hs+x (repro_layer.py:70-83).  One thread owns the
+//   fine index (phase A of gather_fused_kernel)
+//                          ATen upsample_trilinear3d (align_corners=False, scale 1/2) of both coordinate
+//                          volumes, /2, truncate, y*hs+x (repro_layer.py:70-83).  One work item owns the
 //                          <=2x2x2 fine voxels that share the same 8 coarse corners, so the corners are
-//                          loaded once and the separable lerps are shared (bit-identical to ATen's nested
-//                          expression because every intermediate is an fp32 value in both).
+//                          read once and the separable lerps are shared (bit-identical to ATen's nested
+//                          expression because every intermediate is an fp32 value in both).  The indices
+//                          live in shared memory only (the reference materialises them as a 36 MB int64
+//                          tensor); they are written to HBM only when the caller asks for the parity dump.
 //   relayout_kernel        [ncam][K][S][S] planar fp32 -> channels-last [ncam][hs][hs][KP] (fp32 or bf16)
 //                          with the 1-px zero border of F.pad materialised, so that one voxel x camera
 //                          gather is a single contiguous KP-vector instead of K strided scalars.
-//   gather_mean_kernel     index_select + mean over cameras (+ /255): one thread per fine voxel,
-//                          vector loads of the KP-vector per camera, cameras accumulated in order.
+//   gather_fused_kernel    per 8x8x8 voxel tile: coarse corner coordinates of all cameras -> smem, phase A
+//                          above, then phase B = index_select + mean over cameras (+ /255): each thread owns
+//                          two voxels, a warp covers a 4x8 patch of one x-slice (compact pixel footprint ->
+//                          few distinct cache lines per request), vector loads of the KP-vector per camera,
+//                          cameras accumulated in order.  Writes NCDHW fp32 or the bf16 parity-split layout
+//                          of the first tensor-core convolution.
 #include "common.cuh"
 
 namespace jhn {
@@ -77,78 +84,6 @@ coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ i
     bb = __fsub_rn(__fadd_rn(__fsub_rn(bb, chy), fhs), 1.f);
     ca[t] = a;
     cb[t] = bb;
-}
-
-// Per-dimension description of the fine voxels owned by corner block m in [0, h]:
-//   m == 0 : I = {0}         i0 = 0,   lambda1 = 0
-//   m == h : I = {G-1}       i0 = h-1, lambda1 = .25
-//   else   : I = {2m-1, 2m}  i0 = m-1, lambda1 = {.25, .75}
-// (ATen area_pixel_compute_source_index with scale .5: src = .5*(I+.5)-.5 clamped at 0.)
-struct DimBlock { int i0, i1, first, count; float l1[2]; };
-__device__ __forceinline__ DimBlock dim_block(int m, int h)
-{
-    DimBlock d;
-    if (m == 0) { d.i0 = 0; d.first = 0; d.count = 1; d.l1[0] = 0.f; d.l1[1] = 0.f; }
-    else if (m == h) { d.i0 = h - 1; d.first = 2 * h - 1; d.count = 1; d.l1[0] = 0.25f; d.l1[1] = 0.25f; }
-    else { d.i0 = m - 1; d.first = 2 * m - 1; d.count = 2; d.l1[0] = 0.25f; d.l1[1] = 0.75f; }
-    d.i1 = d.i0 + (d.i0 < h - 1 ? 1 : 0);
-    return d;
-}
-
-__global__ void __launch_bounds__(128)
-fine_index_kernel(const float *__restrict__ ca, const float *__restrict__ cb, int BC, int h, int hs,
-                  int lerp_mode, int32_t *__restrict__ idx)
-{
-    const int hb = h + 1, G = 2 * h;
-    const long long total = (long long)BC * hb * hb * hb;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int mk = (int)(t % hb); long long r = t / hb;
-    const int mj = (int)(r % hb); r /= hb;
-    const int mi = (int)(r % hb);
-    const int bc = (int)(r / hb);
-    const DimBlock di = dim_block(mi, h), dj = dim_block(mj, h), dk = dim_block(mk, h);
-    const size_t cbase = (size_t)bc * h * h * h;
-    float va[2][2][2], vb[2][2][2];
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const size_t o = cbase + ((size_t)(p ? di.i1 : di.i0) * h + (q ? dj.i1 : dj.i0)) * h + (s ? dk.i1 : dk.i0);
-                va[p][q][s] = __ldg(ca + o);
-                vb[p][q][s] = __ldg(cb + o);
-            }
-    int32_t *out = idx + (size_t)bc * G * G * G;
-    for (int kv = 0; kv < dk.count; ++kv) {
-        const float lk1 = dk.l1[kv], lk0 = __fsub_rn(1.f, lk1);
-        float xa[2][2], xb[2][2];
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                xa[p][q] = lerp_rn(lk0, va[p][q][0], lk1, va[p][q][1], lerp_mode);
-                xb[p][q] = lerp_rn(lk0, vb[p][q][0], lk1, vb[p][q][1], lerp_mode);
-            }
-        for (int jv = 0; jv < dj.count; ++jv) {
-            const float lj1 = dj.l1[jv], lj0 = __fsub_rn(1.f, lj1);
-            float ya[2], yb[2];
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                ya[p] = lerp_rn(lj0, xa[p][0], lj1, xa[p][1], lerp_mode);
-                yb[p] = lerp_rn(lj0, xb[p][0], lj1, xb[p][1], lerp_mode);
-            }
-            for (int iv = 0; iv < di.count; ++iv) {
-                const float li1 = di.l1[iv], li0 = __fsub_rn(1.f, li1);
-                const float fa = lerp_rn(li0, ya[0], li1, ya[1], lerp_mode);
-                const float fb = lerp_rn(li0, yb[0], li1, yb[1], lerp_mode);
-                const int ix = __float2int_rz(__fmul_rn(fa, 0.5f));      // (val1/2).int()   :82-83
-                const int iy = __float2int_rz(__fmul_rn(fb, 0.5f));
-                out[((size_t)(di.first + iv) * G + (dj.first + jv)) * G + (dk.first + kv)] = iy * hs + ix;
-            }
-        }
-    }
 }
 
 template <typename T> __device__ __forceinline__ T to_store(float v);
@@ -222,59 +157,164 @@ template <> struct Vec<__nv_bfloat16> {
     }
 };
 
+// 8 consecutive channels of one (camera, pixel) KP-vector, added into fp32 accumulators
+__device__ __forceinline__ void add8(const float *p, float *acc)
+{
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    acc[0] = __fadd_rn(acc[0], a.x); acc[1] = __fadd_rn(acc[1], a.y); acc[2] = __fadd_rn(acc[2], a.z); acc[3] = __fadd_rn(acc[3], a.w);
+    acc[4] = __fadd_rn(acc[4], b.x); acc[5] = __fadd_rn(acc[5], b.y); acc[6] = __fadd_rn(acc[6], b.z); acc[7] = __fadd_rn(acc[7], b.w);
+}
+__device__ __forceinline__ void add8(const __nv_bfloat16 *p, float *acc)
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                       // bf16 -> fp32 is a 16-bit shift
+        acc[2 * i + 0] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+constexpr int TS = 8;                                   // voxel tile side
+constexpr int CS = TS / 2 + 2;                          // coarse corners per dimension needed by a tile
+
+// One CTA = one TS^3 tile of fine voxels of frame set blockIdx.y.
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(256)
-gather_mean_kernel(const T *__restrict__ hm, const int32_t *__restrict__ idx, int ncam, int K, int hs, int G,
-                   float post_divide, void *__restrict__ out_)
+gather_fused_kernel(const T *__restrict__ hm, const float *__restrict__ ca, const float *__restrict__ cb, int ncam, int K,
+                    int hs, int G, int lerp_mode, float post_divide, void *__restrict__ out_, int32_t *__restrict__ idx_out)
 {
-    const size_t nv = (size_t)G * G * G;
-    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) uint8_t gsm[];
+    float *co = reinterpret_cast<float *>(gsm);                         // [ncam][2][CS^3] coarse a / b
+    int32_t *ix = reinterpret_cast<int32_t *>(co + (size_t)ncam * 2 * CS * CS * CS);   // [ncam][TS^3]
+    const int h = G / 2, nt = (G + TS - 1) / TS;
     const int b = blockIdx.y;
-    if (v >= nv) return;
-    float acc[KP];
-#pragma unroll
-    for (int i = 0; i < KP; ++i) acc[i] = 0.f;
-    const int32_t *ip = idx + (size_t)b * ncam * nv + v;
-    const T *base = hm + (size_t)b * ncam * hs * hs * KP;
-    for (int c = 0; c < ncam; ++c) {
-        const int32_t flat = __ldg(ip + (size_t)c * nv);
-        Vec<T>::add(base + ((size_t)c * hs * hs + flat) * KP, acc);
+    const int tk = blockIdx.x % nt, tj = (blockIdx.x / nt) % nt, ti = blockIdx.x / (nt * nt);
+    const int I0 = ti * TS, J0 = tj * TS, K0 = tk * TS;
+    const size_t nc = (size_t)h * h * h, nv = (size_t)G * G * G;
+
+    // ---- coarse corners -> smem (indices clamped to the grid; clamped duplicates are what ATen reads too)
+    for (int e = threadIdx.x; e < ncam * CS * CS * CS; e += blockDim.x) {
+        const int lk = e % CS, lj = (e / CS) % CS, li = (e / (CS * CS)) % CS, c = e / (CS * CS * CS);
+        const int gi = min(max(I0 / 2 - 1 + li, 0), h - 1), gj = min(max(J0 / 2 - 1 + lj, 0), h - 1),
+                  gk = min(max(K0 / 2 - 1 + lk, 0), h - 1);
+        const size_t o = ((size_t)b * ncam + c) * nc + ((size_t)gi * h + gj) * h + gk;
+        const int l = (li * CS + lj) * CS + lk;
+        co[(c * 2 + 0) * CS * CS * CS + l] = __ldg(ca + o);
+        co[(c * 2 + 1) * CS * CS * CS + l] = __ldg(cb + o);
     }
-    const float fn = (float)ncam;
+    __syncthreads();
+
+    // ---- phase A: indices of the tile.  Work item = (camera, corner block); block m of a dimension owns the
+    // fine voxels {I0+2m-1 (lambda1 .25), I0+2m (lambda1 .75)} inside the tile, both between corners m and m+1
+    // (ATen area_pixel_compute_source_index, scale .5: src = .5*(I+.5)-.5 clamped at 0, so I=0 has lambda1 0).
+    constexpr int NB = TS / 2 + 1;
+    for (int w = threadIdx.x; w < ncam * NB * NB * NB; w += blockDim.x) {
+        const int mk = w % NB, mj = (w / NB) % NB, mi = (w / (NB * NB)) % NB, c = w / (NB * NB * NB);
+        const float *A = co + (c * 2 + 0) * CS * CS * CS, *Bc = co + (c * 2 + 1) * CS * CS * CS;
+        float va[2][2][2], vb[2][2][2];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        float m = __fdiv_rn(acc[k], fn);                            // torch.mean        :103-105
-        if (post_divide != 1.f) m = __fdiv_rn(m, post_divide);      // heatmaps3D/255.   model.py:72
-        acc[k] = m;
-    }
-    if (LAYOUT == JHN_VOL_NCDHW_F32) {
-        float *out = (float *)out_ + (size_t)b * K * nv + v;
+        for (int p = 0; p < 2; ++p)
 #pragma unroll
-        for (int k = 0; k < KP; ++k)
-            if (k < K) out[(size_t)k * nv] = acc[k];
-    } else {
-        // parity-split, channel-blocked bf16 volume read by the tensor-core front convolution (conv_tc.cu):
-        // [b][s = (I&1,J&1,Kz&1)][j][zp][pp][8] on the G/2 grid; channel chunks beyond K are written as zeros
-        const int I = (int)(v / ((size_t)G * G)), r = (int)(v - (size_t)I * G * G), J = r / G, Kz = r - J * G;
-        const int CJ = (K + 15) / 16 * 2, Wh = G / 2 + 2;
-        const int s = ((I & 1) * 2 + (J & 1)) * 2 + (Kz & 1);
-        uint4 *out = (uint4 *)out_;
-        const size_t pos = ((size_t)(I >> 1) + 1) * Wh * Wh + (size_t)((J >> 1) + 1) * Wh + (Kz >> 1) + 1;
-        const size_t chunk_stride = (size_t)Wh * Wh * Wh;
-        const size_t base = (((size_t)b * 8 + s) * CJ) * chunk_stride + pos;
+            for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j < CJ) {
-                uint32_t pk[4] = {0, 0, 0, 0};
-                if (j < KP / 8) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * j + 2 * i], acc[8 * j + 2 * i + 1]);
-                        pk[i] = *reinterpret_cast<uint32_t *>(&h2);
-                    }
+                for (int r = 0; r < 2; ++r) {
+                    const int l = ((mi + p) * CS + (mj + q)) * CS + (mk + r);
+                    va[p][q][r] = A[l];
+                    vb[p][q][r] = Bc[l];
                 }
-                out[base + (size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {
+            const int lk = 2 * mk - 1 + kv, Kz = K0 + lk;
+            if (lk < 0 || lk >= TS || Kz >= G) continue;
+            const float lk1 = Kz == 0 ? 0.f : (kv ? 0.75f : 0.25f), lk0 = __fsub_rn(1.f, lk1);
+            float xa[2][2], xb[2][2];
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    xa[p][q] = lerp_rn(lk0, va[p][q][0], lk1, va[p][q][1], lerp_mode);
+                    xb[p][q] = lerp_rn(lk0, vb[p][q][0], lk1, vb[p][q][1], lerp_mode);
+                }
+#pragma unroll
+            for (int jv = 0; jv < 2; ++jv) {
+                const int lj = 2 * mj - 1 + jv, J = J0 + lj;
+                if (lj < 0 || lj >= TS || J >= G) continue;
+                const float lj1 = J == 0 ? 0.f : (jv ? 0.75f : 0.25f), lj0 = __fsub_rn(1.f, lj1);
+                float ya[2], yb[2];
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    ya[p] = lerp_rn(lj0, xa[p][0], lj1, xa[p][1], lerp_mode);
+                    yb[p] = lerp_rn(lj0, xb[p][0], lj1, xb[p][1], lerp_mode);
+                }
+#pragma unroll
+                for (int iv = 0; iv < 2; ++iv) {
+                    const int li = 2 * mi - 1 + iv, I = I0 + li;
+                    if (li < 0 || li >= TS || I >= G) continue;
+                    const float li1 = I == 0 ? 0.f : (iv ? 0.75f : 0.25f), li0 = __fsub_rn(1.f, li1);
+                    const float fa = lerp_rn(li0, ya[0], li1, ya[1], lerp_mode);
+                    const float fb = lerp_rn(li0, yb[0], li1, yb[1], lerp_mode);
+                    const int px = __float2int_rz(__fmul_rn(fa, 0.5f));      // (val1/2).int()   :82-83
+                    const int py = __float2int_rz(__fmul_rn(fb, 0.5f));
+                    const int flat = py * hs + px;
+                    ix[c * TS * TS * TS + (li * TS + lj) * TS + lk] = flat;
+                    if (idx_out) idx_out[((size_t)b * ncam + c) * nv + ((size_t)I * G + J) * G + Kz] = flat;
+                }
             }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: gather + camera mean.  Lane = (voxel slot, 8-channel chunk): one warp request covers
+    // 10 voxels x 3 chunks, and the 3 chunk lanes of a voxel read one contiguous 48-byte pixel vector, so a
+    // request touches ~one cache line per distinct pixel instead of one per lane.
+    constexpr int NCH = KP / 8, VPW = 32 / NCH;
+    const T *base = hm + (size_t)b * ncam * hs * hs * KP;
+    const float fn = (float)ncam;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vslot = lane / NCH, j = lane - vslot * NCH;
+#pragma unroll 1
+    for (int g = warp; g * VPW < TS * TS * TS; g += 8) {
+        const int v = g * VPW + vslot;
+        const int lk = v % TS, lj = (v / TS) % TS, li = v / (TS * TS);
+        const int I = I0 + li, J = J0 + lj, Kz = K0 + lk;
+        if (vslot >= VPW || v >= TS * TS * TS || I >= G || J >= G || Kz >= G) continue;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int c = 0; c < ncam; ++c) {
+            const int32_t flat = ix[c * TS * TS * TS + v];
+            add8(base + ((size_t)c * hs * hs + flat) * KP + 8 * j, acc);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float m = __fdiv_rn(acc[k], fn);                            // torch.mean        :103-105
+            if (post_divide != 1.f) m = __fdiv_rn(m, post_divide);      // heatmaps3D/255.   model.py:72
+            acc[k] = m;
+        }
+        if (LAYOUT == JHN_VOL_NCDHW_F32) {
+            float *out = (float *)out_ + (size_t)b * K * nv + ((size_t)I * G + J) * G + Kz;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (8 * j + k < K) out[(size_t)(8 * j + k) * nv] = acc[k];
+        } else {
+            // parity-split, channel-blocked bf16 volume read by the tensor-core front convolution (conv_tc.cu):
+            // [b][s = (I&1,J&1,Kz&1)][j][zp][pp][8] on the G/2 grid; channel chunks beyond K are written as zeros
+            const int CJ = (K + 15) / 16 * 2, Wh = G / 2 + 2;
+            const int sv = ((I & 1) * 2 + (J & 1)) * 2 + (Kz & 1);
+            uint4 *out = (uint4 *)out_;
+            const size_t pos = ((size_t)(I >> 1) + 1) * Wh * Wh + (size_t)((J >> 1) + 1) * Wh + (Kz >> 1) + 1;
+            const size_t chunk_stride = (size_t)Wh * Wh * Wh;
+            const size_t ob = (((size_t)b * 8 + sv) * CJ) * chunk_stride + pos;
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+                pk[i] = *reinterpret_cast<uint32_t *>(&h2);
+            }
+            if (j < CJ) out[ob + (size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (j == 0)
+                for (int jz = NCH; jz < CJ; ++jz) out[ob + (size_t)jz * chunk_stride] = make_uint4(0, 0, 0, 0);
         }
     }
 }
@@ -285,28 +325,35 @@ size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
     Arena a(nullptr, 0);
     a.take<float>((size_t)B * ncam * h * h * h);                    // coarse a
     a.take<float>((size_t)B * ncam * h * h * h);                    // coarse b
-    a.take<int32_t>((size_t)B * ncam * G * G * G);                  // fine indices
     const size_t px = (size_t)B * ncam * hs * hs * KP;
     if (precision == JHN_FP32) a.take<float>(px); else a.take<__nv_bfloat16>(px);
     return a.off;
 }
 
+static size_t gather_smem(int ncam) { return (size_t)ncam * (2 * CS * CS * CS * sizeof(float) + TS * TS * TS * sizeof(int32_t)); }
+
 template <typename T>
-static int run_gather(const ReprojectArgs &a, const T *hm_cl, const int32_t *idx, cudaStream_t st)
+static int run_gather(const ReprojectArgs &a, const T *hm_cl, const float *ca, const float *cb, cudaStream_t st)
 {
-    const size_t nv = (size_t)a.G * a.G * a.G;
-    dim3 grid(cdiv(nv, 256), a.B);
+    const int nt = cdiv(a.G, TS);
+    dim3 grid(nt * nt * nt, a.B);
+    const size_t smem = gather_smem(a.ncam);
+    if (smem > 200 * 1024) return fail(JHN_ERR_SHAPE, "too many cameras (%d) for the gather tile", a.ncam);
     if (a.layout == JHN_VOL_NCDHW_F32) {
-        JHN_LAUNCH("gather_mean_kernel", st,
-                   (gather_mean_kernel<T, JHN_VOL_NCDHW_F32><<<grid, 256, 0, st>>>(hm_cl, idx, a.ncam, a.K, a.hs, a.G,
-                                                                                  a.post_divide, a.volume_out)));
+        auto kern = gather_fused_kernel<T, JHN_VOL_NCDHW_F32>;
+        JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        JHN_LAUNCH("gather_fused_kernel", st,
+                   kern<<<grid, 256, smem, st>>>(hm_cl, ca, cb, a.ncam, a.K, a.hs, a.G, a.lerp_mode, a.post_divide,
+                                                 a.volume_out, a.index_out));
         return JHN_OK;
     }
     const int CJ = (a.K + 15) / 16 * 2;
     JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
-    JHN_LAUNCH("gather_mean_kernel", st,
-               (gather_mean_kernel<T, JHN_VOL_V2V_BF16><<<grid, 256, 0, st>>>(hm_cl, idx, a.ncam, a.K, a.hs, a.G,
-                                                                             a.post_divide, a.volume_out)));
+    auto kern = gather_fused_kernel<T, JHN_VOL_V2V_BF16>;
+    JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    JHN_LAUNCH("gather_fused_kernel", st,
+               kern<<<grid, 256, smem, st>>>(hm_cl, ca, cb, a.ncam, a.K, a.hs, a.G, a.lerp_mode, a.post_divide,
+                                             a.volume_out, a.index_out));
     return JHN_OK;
 }
 
@@ -316,29 +363,24 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
     Arena ar(ws, ws_bytes);
     float *ca = ar.take<float>((size_t)a.B * a.ncam * h * h * h);
     float *cb = ar.take<float>((size_t)a.B * a.ncam * h * h * h);
-    int32_t *idx_ws = ar.take<int32_t>((size_t)a.B * a.ncam * a.G * a.G * a.G);
     const size_t px = (size_t)a.B * a.ncam * a.hs * a.hs * KP;
     void *hm_cl = (a.precision == JHN_FP32) ? (void *)ar.take<float>(px) : (void *)ar.take<__nv_bfloat16>(px);
     if (!ar.ok()) return fail(JHN_ERR_WORKSPACE, "reproject workspace: need %zu bytes, got %zu", ar.off, ws_bytes);
-    int32_t *idx = a.index_out ? a.index_out : idx_ws;
 
     const long long nc = (long long)a.B * a.ncam * h * h * h;
     JHN_LAUNCH("coarse_project_kernel", st,
                coarse_project_kernel<<<cdiv(nc, 256), 256, 0, st>>>(a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B,
                                                                    a.ncam, h, a.spacing, a.hs, ca, cb));
-    const long long nb = (long long)a.B * a.ncam * (h + 1) * (h + 1) * (h + 1);
-    JHN_LAUNCH("fine_index_kernel", st,
-               fine_index_kernel<<<cdiv(nb, 128), 128, 0, st>>>(ca, cb, a.B * a.ncam, h, a.hs, a.lerp_mode, idx));
     const size_t smem = (size_t)a.hs * (KP + 1) * sizeof(float);
     const int rows = a.B * a.ncam * a.hs;
     if (a.precision == JHN_FP32) {
         JHN_LAUNCH("relayout_kernel", st,
                    relayout_kernel<float><<<rows, 128, smem, st>>>(a.heatmaps, a.K, a.hs, a.padded, (float *)hm_cl));
-        return run_gather<float>(a, (const float *)hm_cl, idx, st);
+        return run_gather<float>(a, (const float *)hm_cl, ca, cb, st);
     }
     JHN_LAUNCH("relayout_kernel", st,
                relayout_kernel<__nv_bfloat16><<<rows, 128, smem, st>>>(a.heatmaps, a.K, a.hs, a.padded, (__nv_bfloat16 *)hm_cl));
-    return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, idx, st);
+    return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, ca, cb, st);
 }
 
 }  // namespace jhn
