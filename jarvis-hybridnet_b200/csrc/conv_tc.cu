@@ -26,8 +26,10 @@
 // Weights of the C->C 3x3x3 layers (124 KB bf16) stay resident in shared memory for the CTA's lifetime.
 // The work of a layer is a "stage program" (TcProgram) built on the host: per tile a list of TMA boxes and,
 // per box, the taps (smem row offset, weight index) to issue against it.
+#include <cstdlib>
 #include <cstring>
 
+#include "tc_ptx.cuh"
 #include "v2v.cuh"
 
 namespace jhn {
@@ -36,7 +38,7 @@ namespace jhn {
 // program description shared by host and device
 // ------------------------------------------------------------------------------------------------
 enum { EPI_RAW = 0, EPI_CONVT = 1, EPI_HEAD = 2 };
-constexpr int MAX_STAGES = 12, MAX_TAPS = 9, TILE_M = 128;
+constexpr int MAX_STAGES = 12, MAX_TAPS = 9;
 
 struct TcTap { int16_t aoff, widx; };                 // row offset inside the box; weight tap index
 struct TcStage {
@@ -66,73 +68,6 @@ struct TcLaunch {
     int total_tiles;                                  // B * D * NT * tile_taps
     int Kout;                                         // real output channels (HEAD)
 };
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred = 0;
-    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n.reg .pred P1;\nLAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t *v)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: 8-row x 16-byte core matrices;
-// LBO = byte stride between the two K-chunks of one MMA, SBO = byte stride between 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
-{
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int N)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------------------
 // the implicit-GEMM kernel
@@ -605,9 +540,17 @@ tc_ncdhw_to_bp_kernel(const float *__restrict__ in, uint4 *__restrict__ out, int
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 static inline int tiles_per_plane(int D) { return cdiv((long long)(D - 1) * (D + 2) + D, TILE_M); }
 
+// stacked-x-tap kernel for the C->C 3x3x3 layers (conv3_tc.cu)
+size_t c3_weight_bytes(int NOUT);
+bool c3_plan(int NOUT, int D, int max_smem, int *NS, int *PB);
+int c3_pack(const float *src, __nv_bfloat16 *dst, int cout, int cin, int NOUT, cudaStream_t st);
+int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, float *stats, int B, int D,
+              int NS, int PB, int sms, cudaStream_t st);
+
 struct TcLayer {
     TcProgram prog;
     __nv_bfloat16 *w;
+    __nv_bfloat16 *w3;                                // [dz*3+dy][KC][dx*NOUT+co][8] for the stacked kernel, or null
     float *bias;
     int cin_pad, cout_pad, cout;
     size_t smem_bytes;
@@ -617,7 +560,13 @@ struct TcNet {
     TcLayer layer[NUM_LAYERS];
     void *blob;
     int max_smem;
+    bool legacy_k3;                                   // JHN_CONV3_LEGACY=1: tap-per-MMA kernel for A/B measurements
 };
+
+static bool c3_eligible(const LayerDesc &d, int kind, int cin_pad, int cout_pad)
+{
+    return kind == 0 && cin_pad == cout_pad && cout_pad <= 80 && d.ks == 3;
+}
 
 // Build the stage program of one layer for output/position grid side D.
 // kind: 0 = k3 s1 (BP in), 1 = k3 s2 (PS in), 2 = k2 s2 (PS in), 3 = convT k2 s2 (BP in), 4 = 1x1x1 (BP in)
@@ -716,6 +665,8 @@ int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st)
     JHN_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     TcNet *tc = new TcNet();
     tc->blob = nullptr; tc->max_smem = max_smem;
+    const char *leg = getenv("JHN_CONV3_LEGACY");
+    tc->legacy_k3 = leg && leg[0] == '1';
     net->tc = tc;
     size_t total = 0;
     for (int l = 0; l < NUM_LAYERS; ++l) {
@@ -724,6 +675,7 @@ int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st)
         T.cin_pad = pad16(d.cin); T.cout_pad = pad16(d.cout); T.cout = d.cout;
         const int taps = d.ks * d.ks * d.ks;
         total += align_up((size_t)taps * T.cin_pad * T.cout_pad * 2, 256) + align_up((size_t)T.cout_pad * 4, 256);
+        if (c3_eligible(d, kLayerKind[l], T.cin_pad, T.cout_pad)) total += align_up(c3_weight_bytes(T.cout_pad), 256);
     }
     JHN_CUDA(cudaMalloc(&tc->blob, total));
     char *p = (char *)tc->blob;
@@ -733,6 +685,11 @@ int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st)
         const int taps = d.ks * d.ks * d.ks;
         T.w = (__nv_bfloat16 *)p; p += align_up((size_t)taps * T.cin_pad * T.cout_pad * 2, 256);
         T.bias = (float *)p; p += align_up((size_t)T.cout_pad * 4, 256);
+        T.w3 = nullptr;
+        if (c3_eligible(d, kLayerKind[l], T.cin_pad, T.cout_pad)) {
+            T.w3 = (__nv_bfloat16 *)p; p += align_up(c3_weight_bytes(T.cout_pad), 256);
+            JHN_TRY(c3_pack(tensors[2 * l], T.w3, d.cout, d.cin, T.cout_pad, st));
+        }
         const int n = taps * T.cin_pad * T.cout_pad;
         JHN_LAUNCH("tc_pack_weights_kernel", st,
                    tc_pack_weights_kernel<<<cdiv(n, 256), 256, 0, st>>>(tensors[2 * l], T.w, d.cout, d.cin, taps, d.transposed,
@@ -796,6 +753,10 @@ struct TcCtx {
     int conv(int l, const uint4 *in, int chunks_in, int D, void *out, int chunks_out, float *stats) const
     {
         const TcLayer &T = net->tc->layer[l];
+        int ns = 0, pb = 0;
+        if (T.w3 && !net->tc->legacy_k3 && chunks_in == T.cin_pad / 8 && chunks_out == T.cout_pad / 8 &&
+            c3_plan(T.cout_pad, D, net->tc->max_smem, &ns, &pb))
+            return c3_launch(T.cout_pad, in, T.w3, T.bias, out, stats, B, D, ns, pb, sms, st);
         TcProgram P;
         JHN_TRY(build_program(P, kLayerKind[l], T.cin_pad, T.cout_pad, D, net->tc->max_smem));
         TcLaunch L;
