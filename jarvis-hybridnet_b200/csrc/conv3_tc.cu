@@ -30,9 +30,11 @@
 
 namespace jhn {
 
-constexpr int C3_THREADS = 320;
 constexpr int C3_VALID = TILE_M - 2;                   // output rows per tile
 constexpr int C3_MAX_SLOTS = 8;
+#ifndef C3_EW48
+#define C3_EW48 3                                        // epilogue warps per quadrant for the 48-channel layers
+#endif
 
 struct C3Launch {
     const uint4 *in;                                   // BP bf16 input  [B][KC][D+2][(D+2)^2] 16-byte voxels
@@ -42,6 +44,7 @@ struct C3Launch {
     float *stats;                                      // [B][NOUT][2] or null
     int B, D, NT, total_tiles;
     int NS, PB;                                        // ring slots, positions per plane box
+    int add_bias;                                      // 0 when an InstanceNorm follows (it cancels the bias exactly)
 };
 
 // one 8-column piece of the three dx groups, loaded and waited for in ONE asm statement so that no consumer of
@@ -60,15 +63,18 @@ __device__ __forceinline__ void c3_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, 
         : "memory");
 }
 
-template <int NOUT>
-__global__ void __launch_bounds__(C3_THREADS, 1)
+// EW = epilogue warps per TMEM lane quadrant; each owns NOUT / EW output channels
+template <int NOUT, int EW>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
 tc_conv3_kernel(const C3Launch L)
 {
+    constexpr int C3_THREADS = 64 + 128 * EW;
     constexpr int KC = NOUT / 8;                       // 8-channel chunks of the input (Cin == Cout == NOUT)
     constexpr int N3 = 3 * NOUT;                       // MMA N: three x-taps stacked
-    constexpr int CW = NOUT / 2;                       // output channels per epilogue warp
+    constexpr int CW = NOUT / EW;                      // output channels per epilogue warp
     constexpr int W_BYTES = 9 * KC * N3 * 16;
     static_assert(NOUT % 16 == 0 && N3 <= 256, "stacked N must be a legal tcgen05 N");
+    static_assert(NOUT % (8 * EW) == 0, "channels per epilogue warp must be whole 8-channel chunks");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,7 +94,7 @@ tc_conv3_kernel(const C3Launch L)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < L.NS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * EW); }
         mbar_init(smem_u32(wbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -121,6 +127,11 @@ tc_conv3_kernel(const C3Launch L)
                 for (int dz = fresh ? 0 : 2; dz < 3; ++dz) {
                     mbar_wait(smem_u32(empty + slot), phase ^ 1);
                     const uint32_t fb = smem_u32(full + slot);
+#ifdef C3_DBG_NO_TMA
+                    mbar_arrive(fb);
+                    if (++slot == L.NS) { slot = 0; phase ^= 1; }
+                    continue;
+#endif
                     mbar_expect_tx(fb, run * KC);
                     const uint4 *src = L.in + ((size_t)b * KC * Wp + (z + dz)) * PP + start;
                     uint8_t *dst = ring + (size_t)slot * slot_bytes;
@@ -167,7 +178,9 @@ tc_conv3_kernel(const C3Launch L)
                         for (int kc = 0; kc < KC; kc += 2) {
                             const uint32_t a_lo = lbo_a | (a0 + (uint32_t)(dy * Wp + kc * L.PB));
                             const uint32_t b_lo = lbo_b | (b0 + (uint32_t)((dy * KC + kc) * N3));
+#ifndef C3_DBG_NO_MMA
                             tc_mma_bf16(d_tmem, hi_c | (uint64_t)a_lo, hi_c | (uint64_t)b_lo, idesc, acc);
+#endif
                             acc = 1;
                         }
                     if (dz == 0 || last) tc_commit(smem_u32(empty + slot));   // plane box dead once these MMAs retire
@@ -180,12 +193,12 @@ tc_conv3_kernel(const C3Launch L)
     } else {
         // =================================== epilogue warps =================================
         const int q = warp & 3;                                                // TMEM lane quadrant
-        const int half = (warp - 2) >> 2;                                      // which half of the channels
+        const int part = (warp - 2) >> 2;                                      // which slice of the channels
         const int row = q * 32 + lane;
-        const int c_base = half * CW;
-        float s1[CW], s2[CW];
+        const int c_base = part * CW;
+        float s1[CW], s2[CW], bias_r[CW];
 #pragma unroll
-        for (int i = 0; i < CW; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        for (int i = 0; i < CW; ++i) { s1[i] = 0.f; s2[i] = 0.f; bias_r[i] = L.add_bias ? bias_s[c_base + i] : 0.f; }
         int stat_b = -1;
         auto flush = [&](int b) {
 #pragma unroll
@@ -201,22 +214,40 @@ tc_conv3_kernel(const C3Launch L)
             }
         };
         int ab = 0; uint32_t aphase = 0;
-        int z = t_begin % D, u = t_begin / D;
+        // tile coordinates advance z-fastest; everything that depends on (b, pt) only is refreshed on a column change
+        int z = t_begin % D, pt = (t_begin / D) % L.NT, b = (t_begin / D) / L.NT;
+        bool rowok = false, valid = false;
+        uint4 *optr = nullptr;                                                 // output voxel of this row in plane z, chunk c_base/8
+        bool column_changed = true;
+        const size_t plane_stride = (size_t)PP, chunk_stride = (size_t)Wp * PP;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c_base;
         for (int t = t_begin; t < t_end; ++t) {
-            const int pt = u % L.NT, b = u / L.NT;
-            if (L.stats && b != stat_b) {
-                if (stat_b >= 0) flush(stat_b);
-                stat_b = b;
+            if (column_changed) {
+                if (L.stats && b != stat_b) {
+                    if (stat_b >= 0) flush(stat_b);
+                    stat_b = b;
+                }
+                const int p = Wp + C3_VALID * pt + row;
+                const int yp = p / Wp, xp = p - yp * Wp;
+                rowok = row >= 1 && row <= C3_VALID && p < PP;
+                valid = rowok && xp >= 1 && xp <= D && yp >= 1 && yp <= D;
+                optr = L.out + (((size_t)b * KC + (c_base >> 3)) * Wp + (z + 1)) * plane_stride + p;
+                column_changed = false;
             }
-            const int p = Wp + C3_VALID * pt + row;
-            const int yp = p / Wp, xp = p - yp * Wp;
-            const bool rowok = row >= 1 && row <= C3_VALID && p < PP;
-            const bool valid = rowok && xp >= 1 && xp <= D && yp >= 1 && yp <= D;
             float *xw = xch + (size_t)(t & 1) * 4 * 2 * NOUT;
             mbar_wait(smem_u32(tfull + ab), aphase);
             tc_fence_after();
+#ifdef C3_DBG_NO_EPI
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(tempty + ab));
+            optr += plane_stride;
+            if (++ab == 2) { ab = 0; aphase ^= 1; }
+            if (++z == D) { z = 0; column_changed = true; if (++pt == L.NT) { pt = 0; ++b; } }
+            continue;
+#endif
             float o[CW];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256 + c_base);
+            const uint32_t taddr = taddr0 + (uint32_t)(ab * 256);
 #pragma unroll
             for (int pc = 0; pc < CW / 8; ++pc) {
                 uint32_t d0[8], d1[8], d2[8];
@@ -242,7 +273,7 @@ tc_conv3_kernel(const C3Launch L)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty + ab));                 // accumulator buffer free again
-            asm volatile("bar.sync 1, 256;" ::: "memory");                     // quadrant-boundary rows are in xch
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * EW) : "memory");         // quadrant-boundary rows are in xch
             if (lane == 0 && q > 0) {
 #pragma unroll
                 for (int i = 0; i < CW; ++i) o[i] += xw[((q - 1) * 2 + 0) * NOUT + c_base + i];
@@ -253,13 +284,12 @@ tc_conv3_kernel(const C3Launch L)
             }
 #pragma unroll
             for (int i = 0; i < CW; ++i) {
-                const float v = valid ? o[i] + bias_s[c_base + i] : 0.f;
+                const float v = valid ? o[i] + bias_r[i] : 0.f;
                 o[i] = v;
                 s1[i] += v;
                 s2[i] = fmaf(v, v, s2[i]);
             }
             if (rowok) {
-                const size_t base = (((size_t)b * KC + (c_base >> 3)) * Wp + (z + 1)) * PP + p;
 #pragma unroll
                 for (int j = 0; j < CW / 8; ++j) {
                     uint32_t pk[4];
@@ -268,11 +298,15 @@ tc_conv3_kernel(const C3Launch L)
                         __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * j + 2 * i], o[8 * j + 2 * i + 1]);
                         pk[i] = *reinterpret_cast<uint32_t *>(&h2);
                     }
-                    L.out[base + (size_t)j * Wp * PP] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    optr[(size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
+            optr += plane_stride;
             if (++ab == 2) { ab = 0; aphase ^= 1; }
-            if (++z == D) { z = 0; ++u; }
+            if (++z == D) {
+                z = 0; column_changed = true;
+                if (++pt == L.NT) { pt = 0; ++b; }
+            }
         }
         if (L.stats && stat_b >= 0) flush(stat_b);
     }
@@ -328,7 +362,7 @@ int c3_pack(const float *src, __nv_bfloat16 *dst, int cout, int cin, int NOUT, c
     return JHN_OK;
 }
 
-template <int NOUT>
+template <int NOUT, int EW>
 static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st)
 {
     static bool configured = false;                                            // per instantiation; attribute is per device, set on first use
@@ -338,30 +372,30 @@ static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st
     if (!configured || configured_dev != dev) {
         int max_smem = 0;
         JHN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        JHN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        JHN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<NOUT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true; configured_dev = dev;
     }
-    JHN_LAUNCH("tc_conv3_stacked", st, tc_conv3_kernel<NOUT><<<grid, C3_THREADS, smem, st>>>(L));
+    JHN_LAUNCH("tc_conv3_stacked", st, tc_conv3_kernel<NOUT, EW><<<grid, 64 + 128 * EW, smem, st>>>(L));
     return JHN_OK;
 }
 
 int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, float *stats, int B, int D,
-              int NS, int PB, int sms, cudaStream_t st)
+              int NS, int PB, int sms, int add_bias, cudaStream_t st)
 {
     C3Launch L;
     L.in = (const uint4 *)in; L.w = w; L.bias = bias; L.out = (uint4 *)out; L.stats = stats; L.B = B; L.D = D;
     const int Wp = D + 2;
     L.NT = cdiv((long long)(D - 1) * Wp + D, C3_VALID);
     L.total_tiles = B * L.NT * D;
-    L.NS = NS; L.PB = PB;
+    L.NS = NS; L.PB = PB; L.add_bias = add_bias;
     const size_t smem = c3_weight_bytes(NOUT) + (size_t)NS * (NOUT / 8) * PB * 16 + c3_tail_bytes(NOUT);
     const int grid = L.total_tiles < sms ? L.total_tiles : sms;
     switch (NOUT) {
-    case 16: return c3_launch_t<16>(L, grid, smem, st);
-    case 32: return c3_launch_t<32>(L, grid, smem, st);
-    case 48: return c3_launch_t<48>(L, grid, smem, st);
-    case 64: return c3_launch_t<64>(L, grid, smem, st);
-    case 80: return c3_launch_t<80>(L, grid, smem, st);
+    case 16: return c3_launch_t<16, 2>(L, grid, smem, st);
+    case 32: return c3_launch_t<32, 2>(L, grid, smem, st);
+    case 48: return c3_launch_t<48, C3_EW48>(L, grid, smem, st);
+    case 64: return c3_launch_t<64, 2>(L, grid, smem, st);
+    case 80: return c3_launch_t<80, 2>(L, grid, smem, st);
     }
     return fail(JHN_ERR_SHAPE, "stacked 3x3x3 kernel: unsupported channel width %d", NOUT);
 }

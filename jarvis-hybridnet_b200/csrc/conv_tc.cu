@@ -545,7 +545,7 @@ size_t c3_weight_bytes(int NOUT);
 bool c3_plan(int NOUT, int D, int max_smem, int *NS, int *PB);
 int c3_pack(const float *src, __nv_bfloat16 *dst, int cout, int cin, int NOUT, cudaStream_t st);
 int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, float *stats, int B, int D,
-              int NS, int PB, int sms, cudaStream_t st);
+              int NS, int PB, int sms, int add_bias, cudaStream_t st);
 
 struct TcLayer {
     TcProgram prog;
@@ -748,6 +748,7 @@ size_t tc_workspace(const jhn_v2v *net, int B, int G)
 namespace {
 struct TcCtx {
     const jhn_v2v *net; int B; cudaStream_t st; int sms;
+    bool keep_bias;                                   // debug hook: raw conv output incl. bias; forward: an InstanceNorm follows
 
     // in: BP or PS tensor with `chunks_in` chunks per sample on grid side D (the GEMM-row grid)
     int conv(int l, const uint4 *in, int chunks_in, int D, void *out, int chunks_out, float *stats) const
@@ -756,7 +757,7 @@ struct TcCtx {
         int ns = 0, pb = 0;
         if (T.w3 && !net->tc->legacy_k3 && chunks_in == T.cin_pad / 8 && chunks_out == T.cout_pad / 8 &&
             c3_plan(T.cout_pad, D, net->tc->max_smem, &ns, &pb))
-            return c3_launch(T.cout_pad, in, T.w3, T.bias, out, stats, B, D, ns, pb, sms, st);
+            return c3_launch(T.cout_pad, in, T.w3, T.bias, out, stats, B, D, ns, pb, sms, keep_bias ? 1 : 0, st);
         TcProgram P;
         JHN_TRY(build_program(P, kLayerKind[l], T.cin_pad, T.cout_pad, D, net->tc->max_smem));
         TcLaunch L;
@@ -796,7 +797,7 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
     int dev = 0, sms = 0;
     JHN_CUDA(cudaGetDevice(&dev));
     JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TcCtx c{net, B, st, sms};
+    TcCtx c{net, B, st, sms, false};
     const int j1 = tc->layer[L_FRONT0].cin_pad / 8, j2 = tc->layer[L_FRONT0].cout_pad / 8, j4 = tc->layer[L_POOL].cout_pad / 8;
     const uint4 *vol = (const uint4 *)volume_in;
     if (in_layout != JHN_VOL_V2V_BF16) {
@@ -868,7 +869,7 @@ int tc_debug_layer(const jhn_v2v *net, int l, const float *in, int B, int D, flo
     int dev = 0, sms = 0;
     JHN_CUDA(cudaGetDevice(&dev));
     JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TcCtx c{net, B, st, sms};
+    TcCtx c{net, B, st, sms, true};
     JHN_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 96 * 2 * sizeof(float), st));
     JHN_TRY(c.zero_border(tin, B * (ps ? 8 : 1) * ji, D));
     if (ps) {
