@@ -22,7 +22,10 @@
 //                          few distinct cache lines per request), vector loads of the KP-vector per camera,
 //                          cameras accumulated in order.  Writes NCDHW fp32 or the bf16 parity-split layout
 //                          of the first tensor-core convolution.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace jhn {
 
@@ -86,9 +89,14 @@ coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ i
     cb[t] = bb;
 }
 
+// fp16 staging of the staged gather: values are scaled by 2^-4 (exact) so that the sum over up to 64 cameras
+// of heat-map values as large as 16 000 stays inside the fp16 range; the gather multiplies the sum back.
+constexpr float HALF_STAGE_SCALE = 0.0625f, HALF_STAGE_UNSCALE = 16.f;
+
 template <typename T> __device__ __forceinline__ T to_store(float v);
 template <> __device__ __forceinline__ float to_store<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 to_store<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half to_store<__half>(float v) { return __float2half_rn(v * HALF_STAGE_SCALE); }
 
 // one block per padded image row (b, cam, y): planar -> channels-last through shared memory
 template <typename T>
@@ -319,6 +327,261 @@ gather_fused_kernel(const T *__restrict__ hm, const float *__restrict__ ca, cons
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Staged gather (bf16 throughput path).  One CTA = one 8x8x8 tile of fine voxels, shifted by one voxel
+// (tile t covers fine indices 8t-1 .. 8t+6) so that it is exactly 4x4x4 coarse cells: every cell is the 8
+// fine voxels that interpolate between the same 8 coarse corners, and a tile needs 5^3 corners per camera.
+//
+//   warp 4 (producer)   per camera: the tile's 125 corner coordinates -> shared memory, their min / max ->
+//                       the pixel box that bounds every index of the tile (each ATen lerp is a rounded convex
+//                       combination, so the fine coordinates stay inside the corners' range), then one TMA
+//                       bulk copy (cp.async.bulk, SASS UBLKCP) per box row of the channels-last fp16 staging
+//                       copy into a ring of G_STAGES shared-memory stages, completion on an mbarrier.
+//   warps 0-3 (gather)  thread = (coarse cell, k-parity) = 4 fine voxels sharing the separable lerps:
+//                       indices in registers (bit-identical arithmetic to gather_fused_kernel phase A), then
+//                       per (voxel, camera) three LDS.128 of the pixel's 24-channel fp16 vector and 12 HADD2.
+//                       A quarter-warp is 8 consecutive voxels along z: neighbouring pixels, distinct banks.
+//   The camera sum is accumulated in fp16 (values pre-scaled by 2^-4), converted to fp32 once, then
+//   / ncam, / post_divide as separately rounded fp32 divisions like the fp32 path.  Cameras whose box does
+//   not fit a stage are gathered from global memory instead (same arithmetic).
+// ------------------------------------------------------------------------------------------------
+constexpr int GT = 8, GCELL = GT / 2, GC = GCELL + 1, GC3 = GC * GC * GC;
+constexpr int G_STAGES = 4, G_THREADS = 160;
+constexpr int G_PIX_BYTES = KP * 2;                                           // 48 B per staged pixel
+constexpr int G_CAM_FLOATS = 2 * GC3 + 6;                                     // per camera: corners a / b, then x0 y0 bw fits
+
+template <int MODE> __device__ __forceinline__ float lerp_t(float w0, float a, float w1, float b)
+{
+    if (MODE == JHN_LERP_FMA_FIRST) return __fmaf_rn(w0, a, __fmul_rn(w1, b));
+    if (MODE == JHN_LERP_FMA_SECOND) return __fmaf_rn(w1, b, __fmul_rn(w0, a));
+    return __fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b));
+}
+
+template <int LAYOUT, int MODE>
+__global__ void __launch_bounds__(G_THREADS)
+gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca, const float *__restrict__ cb, int ncam,
+                     int K, int hs, int G, float post_scale, int cap_bytes, void *__restrict__ out_)
+{
+    extern __shared__ __align__(128) uint8_t gsm[];
+    uint8_t *ring = gsm;                                                       // [G_STAGES][cap_bytes] pixel boxes
+    float *cams = reinterpret_cast<float *>(gsm + (size_t)G_STAGES * cap_bytes);   // [ncam][G_CAM_FLOATS]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(cams + (size_t)ncam * G_CAM_FLOATS);
+    uint64_t *full = bars, *empty = bars + G_STAGES;
+    const int h = G / 2, nt = G / GT + 1;
+    const int b = blockIdx.y;
+    const int tk = blockIdx.x % nt, tj = (blockIdx.x / nt) % nt, ti = blockIdx.x / (nt * nt);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t nc = (size_t)h * h * h;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < G_STAGES; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- the tile's 5^3 coarse corners of every camera -> smem (indices clamped to the grid, like ATen's reads)
+    for (int e = threadIdx.x; e < ncam * GC3; e += G_THREADS) {
+        const int c = e / GC3, l = e - c * GC3;
+        const int lk = l % GC, lj = (l / GC) % GC, li = l / (GC * GC);
+        const int gi = min(max(GCELL * ti - 1 + li, 0), h - 1), gj = min(max(GCELL * tj - 1 + lj, 0), h - 1),
+                  gk = min(max(GCELL * tk - 1 + lk, 0), h - 1);
+        const size_t o = ((size_t)b * ncam + c) * nc + ((size_t)gi * h + gj) * h + gk;
+        cams[c * G_CAM_FLOATS + l] = __ldg(ca + o);
+        cams[c * G_CAM_FLOATS + GC3 + l] = __ldg(cb + o);
+    }
+    __syncthreads();
+    // ---- per camera: pixel box bounding every index of the tile (one warp per camera, round robin)
+    for (int c = warp; c < ncam; c += G_THREADS / 32) {
+        const float *A = cams + c * G_CAM_FLOATS;
+        float amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
+        for (int l = lane; l < GC3; l += 32) {
+            const float a = A[l], bb = A[GC3 + l];
+            amin = fminf(amin, a); amax = fmaxf(amax, a); bmin = fminf(bmin, bb); bmax = fmaxf(bmax, bb);
+        }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) {
+            amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, sh)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, sh));
+            bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, sh)); bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, sh));
+        }
+        if (lane == 0) {
+            const int x0 = __float2int_rz(__fmul_rn(amin, 0.5f)), x1 = __float2int_rz(__fmul_rn(amax, 0.5f));
+            const int y0 = __float2int_rz(__fmul_rn(bmin, 0.5f)), y1 = __float2int_rz(__fmul_rn(bmax, 0.5f));
+            const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+            const bool fits = bw * bh * G_PIX_BYTES <= cap_bytes && x0 >= 0 && y0 >= 0 && x1 < hs && y1 < hs;
+            int *mi = reinterpret_cast<int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
+            mi[0] = x0; mi[1] = y0; mi[2] = bw; mi[3] = fits ? bh : 0;
+        }
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        // =================================== producer ========================================
+        for (int c = 0; c < ncam; ++c) {
+            const int s = c % G_STAGES;
+            if (c >= G_STAGES) mbar_wait(smem_u32(empty + s), (uint32_t)((c / G_STAGES) - 1) & 1u);
+            const int *mi = reinterpret_cast<const int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
+            const int x0 = mi[0], y0 = mi[1], bw = mi[2], bh = mi[3];
+            const uint32_t fb = smem_u32(full + s);
+            if (bh == 0) {                                                     // box does not fit: gathered from global memory
+                if (lane == 0) mbar_arrive(fb);
+                continue;
+            }
+            const uint32_t row_bytes = (uint32_t)(bw * G_PIX_BYTES);
+            if (lane == 0) mbar_expect_tx(fb, row_bytes * (uint32_t)bh);
+            __syncwarp();
+            uint8_t *box = ring + (size_t)s * cap_bytes;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(hm) + ((((size_t)b * ncam + c) * hs + y0) * hs + x0) * G_PIX_BYTES;
+            for (int r = lane; r < bh; r += 32)
+                bulk_load(smem_u32(box + (size_t)r * row_bytes), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
+        }
+        return;
+    }
+
+    // =================================== gather warps ========================================
+    const int ci = warp, cj = lane >> 3, ck = (lane >> 1) & 3, kv = lane & 1;
+    const int I0 = GT * ti - 1 + 2 * ci, J0 = GT * tj - 1 + 2 * cj, Kz = GT * tk - 1 + 2 * ck + kv;
+    // ATen area_pixel_compute_source_index, scale .5: odd fine index -> lambda1 .25, even -> .75, index 0 -> 0
+    const float lk1 = Kz == 0 ? 0.f : (kv ? 0.75f : 0.25f), lk0 = __fsub_rn(1.f, lk1);
+    float lj1[2], lj0[2], li1[2], li0[2];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        lj1[v] = (J0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f); lj0[v] = __fsub_rn(1.f, lj1[v]);
+        li1[v] = (I0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f); li0[v] = __fsub_rn(1.f, li1[v]);
+    }
+    __half2 acc[4][KP / 2];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int i = 0; i < KP / 2; ++i) acc[v][i] = __float2half2_rn(0.f);
+    const int l0 = (ci * GC + cj) * GC + ck;
+
+    for (int c = 0; c < ncam; ++c) {
+        const int s = c % G_STAGES;
+        const float *A = cams + c * G_CAM_FLOATS + l0, *Bc = A + GC3;
+        const int *mi = reinterpret_cast<const int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
+        const int x0 = mi[0], y0 = mi[1], bw = mi[2], fits = mi[3];
+        // indices of this thread's four voxels (registers only; same arithmetic as gather_fused_kernel phase A)
+        float xa[2][2], xb[2][2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int l = (p * GC + q) * GC;
+                xa[p][q] = lerp_t<MODE>(lk0, A[l], lk1, A[l + 1]);
+                xb[p][q] = lerp_t<MODE>(lk0, Bc[l], lk1, Bc[l + 1]);
+            }
+        int off[4];
+#pragma unroll
+        for (int jv = 0; jv < 2; ++jv) {
+            float ya[2], yb[2];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                ya[p] = lerp_t<MODE>(lj0[jv], xa[p][0], lj1[jv], xa[p][1]);
+                yb[p] = lerp_t<MODE>(lj0[jv], xb[p][0], lj1[jv], xb[p][1]);
+            }
+#pragma unroll
+            for (int iv = 0; iv < 2; ++iv) {
+                const float fa = lerp_t<MODE>(li0[iv], ya[0], li1[iv], ya[1]);
+                const float fb2 = lerp_t<MODE>(li0[iv], yb[0], li1[iv], yb[1]);
+                const int px = __float2int_rz(__fmul_rn(fa, 0.5f));                      // (val/2).int()   repro_layer.py:82-83
+                const int py = __float2int_rz(__fmul_rn(fb2, 0.5f));
+                off[iv * 2 + jv] = fits ? ((py - y0) * bw + (px - x0)) * G_PIX_BYTES : (py * hs + px) * G_PIX_BYTES;
+            }
+        }
+        mbar_wait(smem_u32(full + s), (uint32_t)(c / G_STAGES) & 1u);
+        uint4 w[4][3];
+        if (fits) {
+            const uint8_t *box = ring + (size_t)s * cap_bytes;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const uint4 *pp = reinterpret_cast<const uint4 *>(box + off[v]);
+                w[v][0] = pp[0]; w[v][1] = pp[1]; w[v][2] = pp[2];
+            }
+        } else {
+            const uint8_t *gbase = reinterpret_cast<const uint8_t *>(hm) + ((size_t)b * ncam + c) * hs * hs * G_PIX_BYTES;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const uint4 *pp = reinterpret_cast<const uint4 *>(gbase + off[v]);
+                w[v][0] = __ldg(pp); w[v][1] = __ldg(pp + 1); w[v][2] = __ldg(pp + 2);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const uint32_t ww[4] = {w[v][g].x, w[v][g].y, w[v][g].z, w[v][g].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[v][4 * g + i] = __hadd2(acc[v][4 * g + i], *reinterpret_cast<const __half2 *>(&ww[i]));
+            }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(empty + s));
+    }
+
+    // ---- mean over cameras (+ /255) as one fp32 scale, store ---------------------------------------
+    const size_t nv = (size_t)G * G * G;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int I = I0 + (v >> 1), J = J0 + (v & 1);
+        if (I < 0 || J < 0 || Kz < 0 || I >= G || J >= G || Kz >= G) continue;
+        float m[KP];
+#pragma unroll
+        for (int i = 0; i < KP / 2; ++i) {
+            const float2 f = __half22float2(acc[v][i]);
+            m[2 * i] = f.x * post_scale; m[2 * i + 1] = f.y * post_scale;
+        }
+        if (LAYOUT == JHN_VOL_NCDHW_F32) {
+            float *out = (float *)out_ + (size_t)b * K * nv + ((size_t)I * G + J) * G + Kz;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) out[(size_t)k * nv] = m[k];
+        } else {
+            const int CJ = (K + 15) / 16 * 2, Wh = G / 2 + 2;
+            const int sv = ((I & 1) * 2 + (J & 1)) * 2 + (Kz & 1);
+            uint4 *out = (uint4 *)out_;
+            const size_t pos = ((size_t)(I >> 1) + 1) * Wh * Wh + (size_t)((J >> 1) + 1) * Wh + (Kz >> 1) + 1;
+            const size_t chunk_stride = (size_t)Wh * Wh * Wh;
+            const size_t ob = (((size_t)b * 8 + sv) * CJ) * chunk_stride + pos;
+#pragma unroll
+            for (int j = 0; j < KP / 8; ++j) {
+                if (j < CJ) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(m[8 * j + 2 * i], m[8 * j + 2 * i + 1]);
+                        pk[i] = *reinterpret_cast<uint32_t *>(&h2);
+                    }
+                    out[ob + (size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            for (int jz = KP / 8; jz < CJ; ++jz) out[ob + (size_t)jz * chunk_stride] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+template <int LAYOUT>
+static int launch_staged(const ReprojectArgs &a, const __half *hm_cl, const float *ca, const float *cb, int cap, cudaStream_t st)
+{
+    const size_t gsmem = (size_t)G_STAGES * cap + (size_t)a.ncam * G_CAM_FLOATS * 4 + 2 * G_STAGES * 8;
+    if (gsmem > 200 * 1024) return fail(JHN_ERR_SHAPE, "too many cameras (%d) for the staged gather", a.ncam);
+    const int nt = a.G / GT + 1;
+    dim3 grid(nt * nt * nt, a.B);
+    // the bf16 volume hides a 1-ulp difference between x/ncam/post_divide and x*(1/(ncam*post_divide)); 16 undoes the fp16 pre-scale
+    const float post_scale = HALF_STAGE_UNSCALE / ((float)a.ncam * a.post_divide);
+#define JHN_STAGED(MODE)                                                                                         \
+    {                                                                                                            \
+        auto kern = gather_staged_kernel<LAYOUT, MODE>;                                                          \
+        JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));           \
+        JHN_LAUNCH("gather_staged_kernel", st,                                                                   \
+                   kern<<<grid, G_THREADS, gsmem, st>>>(hm_cl, ca, cb, a.ncam, a.K, a.hs, a.G, post_scale, cap, a.volume_out)); \
+        return JHN_OK;                                                                                           \
+    }
+    if (a.lerp_mode == JHN_LERP_FMA_FIRST) JHN_STAGED(JHN_LERP_FMA_FIRST)
+    if (a.lerp_mode == JHN_LERP_FMA_SECOND) JHN_STAGED(JHN_LERP_FMA_SECOND)
+    JHN_STAGED(JHN_LERP_NO_FMA)
+#undef JHN_STAGED
+}
+
+static int pick_gather_cap(int) { return 12288; }                             // bytes of pixel box per ring stage
+
 size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
 {
     const int h = G / 2;
@@ -377,6 +640,16 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
         JHN_LAUNCH("relayout_kernel", st,
                    relayout_kernel<float><<<rows, 128, smem, st>>>(a.heatmaps, a.K, a.hs, a.padded, (float *)hm_cl));
         return run_gather<float>(a, (const float *)hm_cl, ca, cb, st);
+    }
+    if (!a.index_out && a.G % GT == 0) {
+        // throughput path: fp16 staging copy + staged gather (the index dump needs the in-order kernel below)
+        JHN_LAUNCH("relayout_kernel", st,
+                   relayout_kernel<__half><<<rows, 128, smem, st>>>(a.heatmaps, a.K, a.hs, a.padded, (__half *)hm_cl));
+        const int cap = pick_gather_cap(a.hs);
+        if (a.layout == JHN_VOL_NCDHW_F32) return launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, ca, cb, cap, st);
+        const int CJ = (a.K + 15) / 16 * 2;
+        JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
+        return launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, ca, cb, cap, st);
     }
     JHN_LAUNCH("relayout_kernel", st,
                relayout_kernel<__nv_bfloat16><<<rows, 128, smem, st>>>(a.heatmaps, a.K, a.hs, a.padded, (__nv_bfloat16 *)hm_cl));
