@@ -110,6 +110,10 @@ int jhn_reproject_gather(const float *heatmaps, int heatmaps_padded,
 int jhn_v2v_create(const float *const *tensors, int num_tensors, int K, int precision,
                    jhn_stream_t stream, jhn_v2v **out);
 void jhn_v2v_destroy(jhn_v2v *net);
+/* Promise (on=1) that the workspace handed to jhn_v2v_forward / jhn_hybrid3d_forward with this network is
+ * written by nobody else between calls.  The bf16 path then clears the zero borders of its padded activation
+ * tensors only when the workspace pointer or the shape changes instead of on every call.  Default: off. */
+int jhn_v2v_set_workspace_persistent(jhn_v2v *net, int on);
 int jhn_v2v_workspace_bytes(const jhn_v2v *net, int B, int G, size_t *bytes);
 int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G,
                     float *out, void *workspace, size_t workspace_bytes, jhn_stream_t stream);

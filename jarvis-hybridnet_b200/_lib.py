@@ -23,6 +23,7 @@ SYMBOLS = {
                                      c_int, c_float, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "jhn_v2v_create": (c_int, [POINTER(_P), c_int, c_int, c_int, _P, POINTER(_P)]),
     "jhn_v2v_destroy": (None, [_P]),
+    "jhn_v2v_set_workspace_persistent": (c_int, [_P, c_int]),
     "jhn_v2v_workspace_bytes": (c_int, [_P, c_int, c_int, POINTER(c_size_t)]),
     "jhn_v2v_forward": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "jhn_v2v_debug_layer_workspace_bytes": (c_int, [_P, c_int, c_int, c_int, POINTER(c_size_t)]),

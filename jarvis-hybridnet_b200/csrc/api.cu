@@ -81,7 +81,7 @@ using namespace jhn;
 extern "C" {
 
 const char *jhn_last_error(void) { return g_err; }
-int jhn_abi_version(void) { return 1; }
+int jhn_abi_version(void) { return 2; }
 unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
@@ -140,7 +140,7 @@ int jhn_reproject_gather(const float *heatmaps, int heatmaps_padded, const float
     if (((uintptr_t)workspace & 255) != 0) return fail(JHN_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     ReprojectArgs a{heatmaps, heatmaps_padded ? 1 : 0, cameraMatrices, intrinsicMatrices, distortionCoefficients,
                     center3D, centerHM, B, ncam, K, hs, G, spacing, lerp_mode, post_divide, precision, layout,
-                    volume_out, index_out};
+                    volume_out, index_out, 0};
     return reproject_launch(a, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -159,11 +159,21 @@ int jhn_v2v_create(const float *const *tensors, int num_tensors, int K, int prec
     jhn_v2v *net = new (std::nothrow) jhn_v2v();
     if (!net) return fail(JHN_ERR_CUDA, "out of host memory");
     net->K = K; net->precision = precision; net->device = dev; net->blob = nullptr; net->tc = nullptr;
+    net->ws_persistent = 0; net->z_ws = nullptr; net->z_B = net->z_G = 0; net->z_kind = -1;
+    net->zv_ptr = nullptr; net->zv_B = net->zv_G = 0;
     layer_table(K, net->desc);
     int s = v2v_f32_pack(net, tensors, (cudaStream_t)stream);
     if (s == JHN_OK && precision == JHN_BF16) s = tc_create(net, tensors, (cudaStream_t)stream);
     if (s != JHN_OK) { jhn_v2v_destroy(net); return s; }
     *out = net;
+    return JHN_OK;
+}
+
+int jhn_v2v_set_workspace_persistent(jhn_v2v *net, int on)
+{
+    if (!net) return fail(JHN_ERR_ARG, "net is null");
+    net->ws_persistent = on ? 1 : 0;
+    net->z_ws = nullptr; net->zv_ptr = nullptr;
     return JHN_OK;
 }
 
@@ -264,9 +274,17 @@ int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps
     JHN_TRY(jhn_v2v_workspace_bytes(net, B, G, &v2v));
     void *ws_v = p; p += align_up(v2v, 256);
     float *vout = (float *)p;
-    JHN_TRY(jhn_reproject_gather(heatmaps, heatmaps_padded, cameraMatrices, intrinsicMatrices, distortionCoefficients,
-                                 center3D, centerHM, B, ncam, net->K, hs, G, spacing, lerp_mode, 255.f, net->precision,
-                                 hybrid_layout(net), vol, nullptr, ws_r, rws, stream));
+    if (!heatmaps || !cameraMatrices || !intrinsicMatrices || !distortionCoefficients || !center3D || !centerHM || !points || !conf)
+        return fail(JHN_ERR_ARG, "jhn_hybrid3d_forward: null pointer argument");
+    if (lerp_mode < 0 || lerp_mode > 2) return fail(JHN_ERR_ARG, "lerp_mode %d not in {0,1,2}", lerp_mode);
+    ReprojectArgs ra{heatmaps, heatmaps_padded ? 1 : 0, cameraMatrices, intrinsicMatrices, distortionCoefficients,
+                     center3D, centerHM, B, ncam, net->K, hs, G, spacing, lerp_mode, 255.f, net->precision, hybrid_layout(net),
+                     vol, nullptr, 0};
+    if (net->precision == JHN_BF16) {
+        ra.borders_valid = net->ws_persistent && net->zv_ptr == vol && net->zv_B == B && net->zv_G == G;
+        net->zv_ptr = vol; net->zv_B = B; net->zv_G = G;
+    }
+    JHN_TRY(reproject_launch(ra, ws_r, rws, (cudaStream_t)stream));
     JHN_TRY(jhn_v2v_forward(net, vol, hybrid_layout(net), B, G, vout, ws_v, align_up(v2v, 256), stream));
     return jhn_centroid_reduce(vout, B, net->K, h, spacing, roi, center3D, points, conf, argmax, stream);
 }

@@ -73,6 +73,7 @@ struct ReprojectArgs {
     float spacing; int lerp_mode; float post_divide;
     int precision, layout;
     void *volume_out; int32_t *index_out;
+    int borders_valid;     // V2V-layout volume: zero border already in place (hybrid path, persistent workspace)
 };
 size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision);
 int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStream_t st);

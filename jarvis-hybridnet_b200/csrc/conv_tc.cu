@@ -800,15 +800,16 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
     TcCtx c{net, B, st, sms, false};
     const int j1 = tc->layer[L_FRONT0].cin_pad / 8, j2 = tc->layer[L_FRONT0].cout_pad / 8, j4 = tc->layer[L_POOL].cout_pad / 8;
     const uint4 *vol = (const uint4 *)volume_in;
+    const bool borders_valid = net->ws_persistent && net->z_ws == ws && net->z_B == B && net->z_G == G && net->z_kind == in_layout;
     if (in_layout != JHN_VOL_V2V_BF16) {
-        JHN_TRY(c.zero_border(t.vol_ps, B * 8 * j1, h));
+        if (!borders_valid) JHN_TRY(c.zero_border(t.vol_ps, B * 8 * j1, h));
         const size_t nv = (size_t)G * G * G;
         JHN_LAUNCH("tc_ncdhw_to_ps_kernel", st,
                    tc_ncdhw_to_ps_kernel<<<dim3(cdiv(nv, 256), B * j1), 256, 0, st>>>((const float *)volume_in, t.vol_ps, net->K, G, j1));
         vol = t.vol_ps;
     }
     JHN_CUDA(cudaMemsetAsync(t.stats, 0, (size_t)11 * B * 96 * 2 * sizeof(float), st));
-    {
+    if (!borders_valid) {
         ZeroJobs J;
         uint4 *ptrs[9] = {t.A, t.Bq, t.C, t.Dd, t.E, t.Pq, t.Q, t.R, t.Xps};
         const int chunks[9] = {B * j2, B * j2, B * j2, B * j2, B * j2, B * j4, B * j4, B * j4, B * 8 * j2};
@@ -818,6 +819,7 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
         for (int i = 0; i < 9; ++i) { J.first[i] = total; J.D[i] = sides[i]; J.p[i] = ptrs[i]; total += chunks[i] * (sides[i] + 2); }
         J.first[9] = total;
         JHN_LAUNCH("tc_zero_border_kernel", st, tc_zero_border_multi_kernel<<<total, 128, 0, st>>>(J));
+        net->z_ws = ws; net->z_B = B; net->z_G = G; net->z_kind = in_layout;
     }
     auto S = [&](int i) { return t.stats + (size_t)i * B * 96 * 2; };
 

@@ -611,7 +611,7 @@ static int run_gather(const ReprojectArgs &a, const T *hm_cl, const float *ca, c
         return JHN_OK;
     }
     const int CJ = (a.K + 15) / 16 * 2;
-    JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
+    if (!a.borders_valid) JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
     auto kern = gather_fused_kernel<T, JHN_VOL_V2V_BF16>;
     JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     JHN_LAUNCH("gather_fused_kernel", st,
@@ -648,7 +648,7 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
         const int cap = pick_gather_cap(a.hs);
         if (a.layout == JHN_VOL_NCDHW_F32) return launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, ca, cb, cap, st);
         const int CJ = (a.K + 15) / 16 * 2;
-        JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
+        if (!a.borders_valid) JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
         return launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, ca, cb, cap, st);
     }
     JHN_LAUNCH("relayout_kernel", st,

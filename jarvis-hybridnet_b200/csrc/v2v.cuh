@@ -25,6 +25,13 @@ struct jhn_v2v {
     jhn::LayerF32 f32[jhn::NUM_LAYERS];
     float *blob;             // one allocation behind all fp32 packed tensors
     jhn::TcNet *tc;          // non-null iff precision == JHN_BF16
+    // Zero-border cache (jhn_v2v_set_workspace_persistent): the padded bf16 tensors keep their zero borders from
+    // one forward to the next because every kernel writes zeros (or nothing) there, so they are cleared only
+    // when the workspace pointer or the shape changes.  Off by default: the caller must promise that nobody
+    // else writes the workspace between calls.
+    mutable int ws_persistent;
+    mutable const void *z_ws; mutable int z_B, z_G, z_kind;       // tensors of tc_forward
+    mutable const void *zv_ptr; mutable int zv_B, zv_G;           // V2V-layout volume written by the reprojection stage
 };
 
 namespace jhn {

@@ -60,6 +60,9 @@ class V2VNet(nn.Module):
             _lib.check(lib.jhn_v2v_create(arr, len(keep), self.K, self.precision, _lib.stream_ptr(),
                                           ctypes.byref(out)))
             torch.cuda.current_stream().synchronize()      # packing reads `keep`
+            # the workspaces handed to this handle are private tensors of the wrapper modules (V2VNet._ws,
+            # HybridNet3D._ws): nobody else writes them, so the zero borders may be cached between calls
+            _lib.check(lib.jhn_v2v_set_workspace_persistent(out, 1))
             self._handle, self._handle_key = out, key
         return self._handle
 
