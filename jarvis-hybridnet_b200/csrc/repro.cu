@@ -98,35 +98,6 @@ template <> __device__ __forceinline__ float to_store<float>(float v) { return v
 template <> __device__ __forceinline__ __nv_bfloat16 to_store<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half to_store<__half>(float v) { return __float2half_rn(v * HALF_STAGE_SCALE); }
 
-// one block per padded image row (b, cam, y): planar -> channels-last through shared memory
-template <typename T>
-__global__ void __launch_bounds__(128)
-relayout_kernel(const float *__restrict__ in, int K, int hs, int padded, T *__restrict__ out)
-{
-    extern __shared__ float tile[];                     // [hs][KP+1]
-    const int y = blockIdx.x % hs;
-    const int bc = blockIdx.x / hs;
-    const int S = padded ? hs : hs - 2;
-    const int off = padded ? 0 : 1;
-    const int ys = y - off;
-    const bool row_ok = ys >= 0 && ys < S;
-    for (int k = 0; k < K; ++k) {
-        const float *src = in + (((size_t)bc * K + k) * S + (row_ok ? ys : 0)) * S;
-        for (int x = threadIdx.x; x < hs; x += blockDim.x) {
-            const int xs = x - off;
-            float v = 0.f;
-            if (row_ok && xs >= 0 && xs < S) v = __ldg(src + xs);
-            tile[x * (KP + 1) + k] = v;
-        }
-    }
-    __syncthreads();
-    T *dst = out + ((size_t)bc * hs + y) * hs * KP;
-    for (int e = threadIdx.x; e < hs * KP; e += blockDim.x) {
-        const int x = e / KP, k = e - x * KP;
-        dst[e] = to_store<T>(k < K ? tile[x * (KP + 1) + k] : 0.f);
-    }
-}
-
 template <typename T> struct Vec;
 template <> struct Vec<float> {
     static constexpr int N = KP / 4;                    // 6 x float4
@@ -181,6 +152,50 @@ __device__ __forceinline__ void add8(const __nv_bfloat16 *p, float *acc)
         acc[2 * i + 0] += __uint_as_float(w[i] << 16);
         acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
     }
+}
+
+// planar -> channels-last without shared memory: one thread per padded pixel reads its K channel values (for a
+// fixed channel the lanes of a warp read consecutive floats: coalesced, K independent loads in flight per
+// thread) and writes the KP-vector as 16-byte stores; the three / six stores of a warp fill whole lines in L2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+relayout_pixel_kernel(const float *__restrict__ in, int K, int hs, int padded, long long npix, T *__restrict__ out)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix) return;
+    const int hh = hs * hs;
+    const long long bc = idx / hh;
+    const int r = (int)(idx - bc * hh), y = r / hs, x = r - y * hs;
+    const int S = padded ? hs : hs - 2, off = padded ? 0 : 1;
+    const int ys = y - off, xs = x - off;
+    const bool inside = ys >= 0 && ys < S && xs >= 0 && xs < S;
+    float v[KP];
+    const float *src = in + ((size_t)bc * K * S + (inside ? ys : 0)) * S + (inside ? xs : 0);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) v[k] = (inside && k < K) ? __ldg(src + (size_t)k * S * S) : 0.f;
+    T *dst = out + (size_t)idx * KP;
+    if (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < KP / 4; ++i)
+            reinterpret_cast<float4 *>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < KP / 8; ++i) {
+            T t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = to_store<T>(v[8 * i + j]);
+            reinterpret_cast<uint4 *>(dst)[i] = *reinterpret_cast<const uint4 *>(t);
+        }
+    }
+}
+
+template <typename T>
+static int launch_relayout(const ReprojectArgs &a, T *hm_cl, cudaStream_t st)
+{
+    const long long npix = (long long)a.B * a.ncam * a.hs * a.hs;
+    JHN_LAUNCH("relayout_kernel", st,
+               relayout_pixel_kernel<T><<<cdiv(npix, 256), 256, 0, st>>>(a.heatmaps, a.K, a.hs, a.padded, npix, hm_cl));
+    return JHN_OK;
 }
 
 constexpr int TS = 8;                                   // voxel tile side
@@ -347,9 +362,15 @@ gather_fused_kernel(const T *__restrict__ hm, const float *__restrict__ ca, cons
 //   not fit a stage are gathered from global memory instead (same arithmetic).
 // ------------------------------------------------------------------------------------------------
 constexpr int GT = 8, GCELL = GT / 2, GC = GCELL + 1, GC3 = GC * GC * GC;
-constexpr int G_STAGES = 4, G_THREADS = 160;
+#ifndef JHN_G_STAGES
+#define JHN_G_STAGES 4
+#endif
+#ifndef JHN_G_MINBLOCKS
+#define JHN_G_MINBLOCKS 3
+#endif
+constexpr int G_STAGES = JHN_G_STAGES, G_THREADS = 160;
 constexpr int G_PIX_BYTES = KP * 2;                                           // 48 B per staged pixel
-constexpr int G_CAM_FLOATS = 2 * GC3 + 6;                                     // per camera: corners a / b, then x0 y0 bw fits
+constexpr int G_CAM_FLOATS = 2 * GC3 + 6;                                     // per camera: corners a / b, then x0 y0 bw bh|0 pitch
 
 template <int MODE> __device__ __forceinline__ float lerp_t(float w0, float a, float w1, float b)
 {
@@ -359,7 +380,7 @@ template <int MODE> __device__ __forceinline__ float lerp_t(float w0, float a, f
 }
 
 template <int LAYOUT, int MODE>
-__global__ void __launch_bounds__(G_THREADS)
+__global__ void __launch_bounds__(G_THREADS, JHN_G_MINBLOCKS)
 gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca, const float *__restrict__ cb, int ncam,
                      int K, int hs, int G, float post_scale, int cap_bytes, void *__restrict__ out_)
 {
@@ -406,9 +427,14 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
             const int x0 = __float2int_rz(__fmul_rn(amin, 0.5f)), x1 = __float2int_rz(__fmul_rn(amax, 0.5f));
             const int y0 = __float2int_rz(__fmul_rn(bmin, 0.5f)), y1 = __float2int_rz(__fmul_rn(bmax, 0.5f));
             const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-            const bool fits = bw * bh * G_PIX_BYTES <= cap_bytes && x0 >= 0 && y0 >= 0 && x1 < hs && y1 < hs;
+            // smem row pitch in pixels, == 3 or 5 (mod 8): a pixel vector is three 16-byte bank groups, so two
+            // pixels collide iff their linear offsets differ by a multiple of 8; with such a pitch the short
+            // pixel runs a quarter-warp (8 voxels along z) touches almost never do
+            int pitch = bw;
+            while ((pitch & 7) != 3 && (pitch & 7) != 5) ++pitch;
+            const bool fits = pitch * bh * G_PIX_BYTES <= cap_bytes && x0 >= 0 && y0 >= 0 && x1 < hs && y1 < hs;
             int *mi = reinterpret_cast<int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-            mi[0] = x0; mi[1] = y0; mi[2] = bw; mi[3] = fits ? bh : 0;
+            mi[0] = x0; mi[1] = y0; mi[2] = bw; mi[3] = fits ? bh : 0; mi[4] = pitch;
         }
     }
     __syncthreads();
@@ -419,7 +445,7 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
             const int s = c % G_STAGES;
             if (c >= G_STAGES) mbar_wait(smem_u32(empty + s), (uint32_t)((c / G_STAGES) - 1) & 1u);
             const int *mi = reinterpret_cast<const int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-            const int x0 = mi[0], y0 = mi[1], bw = mi[2], bh = mi[3];
+            const int x0 = mi[0], y0 = mi[1], bw = mi[2], bh = mi[3], pitch = mi[4];
             const uint32_t fb = smem_u32(full + s);
             if (bh == 0) {                                                     // box does not fit: gathered from global memory
                 if (lane == 0) mbar_arrive(fb);
@@ -431,7 +457,7 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
             uint8_t *box = ring + (size_t)s * cap_bytes;
             const uint8_t *src = reinterpret_cast<const uint8_t *>(hm) + ((((size_t)b * ncam + c) * hs + y0) * hs + x0) * G_PIX_BYTES;
             for (int r = lane; r < bh; r += 32)
-                bulk_load(smem_u32(box + (size_t)r * row_bytes), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
+                bulk_load(smem_u32(box + (size_t)r * pitch * G_PIX_BYTES), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
         }
         return;
     }
@@ -458,7 +484,7 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
         const int s = c % G_STAGES;
         const float *A = cams + c * G_CAM_FLOATS + l0, *Bc = A + GC3;
         const int *mi = reinterpret_cast<const int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-        const int x0 = mi[0], y0 = mi[1], bw = mi[2], fits = mi[3];
+        const int x0 = mi[0], y0 = mi[1], fits = mi[3], bw = mi[4];                  // bw: smem row pitch from here on
         // indices of this thread's four voxels (registers only; same arithmetic as gather_fused_kernel phase A)
         float xa[2][2], xb[2][2];
 #pragma unroll
@@ -634,25 +660,20 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
     JHN_LAUNCH("coarse_project_kernel", st,
                coarse_project_kernel<<<cdiv(nc, 256), 256, 0, st>>>(a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B,
                                                                    a.ncam, h, a.spacing, a.hs, ca, cb));
-    const size_t smem = (size_t)a.hs * (KP + 1) * sizeof(float);
-    const int rows = a.B * a.ncam * a.hs;
     if (a.precision == JHN_FP32) {
-        JHN_LAUNCH("relayout_kernel", st,
-                   relayout_kernel<float><<<rows, 128, smem, st>>>(a.heatmaps, a.K, a.hs, a.padded, (float *)hm_cl));
+        JHN_TRY(launch_relayout<float>(a, (float *)hm_cl, st));
         return run_gather<float>(a, (const float *)hm_cl, ca, cb, st);
     }
     if (!a.index_out && a.G % GT == 0) {
         // throughput path: fp16 staging copy + staged gather (the index dump needs the in-order kernel below)
-        JHN_LAUNCH("relayout_kernel", st,
-                   relayout_kernel<__half><<<rows, 128, smem, st>>>(a.heatmaps, a.K, a.hs, a.padded, (__half *)hm_cl));
+        JHN_TRY(launch_relayout<__half>(a, (__half *)hm_cl, st));
         const int cap = pick_gather_cap(a.hs);
         if (a.layout == JHN_VOL_NCDHW_F32) return launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, ca, cb, cap, st);
         const int CJ = (a.K + 15) / 16 * 2;
         if (!a.borders_valid) JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
         return launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, ca, cb, cap, st);
     }
-    JHN_LAUNCH("relayout_kernel", st,
-               relayout_kernel<__nv_bfloat16><<<rows, 128, smem, st>>>(a.heatmaps, a.K, a.hs, a.padded, (__nv_bfloat16 *)hm_cl));
+    JHN_TRY(launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)hm_cl, st));
     return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, ca, cb, st);
 }
 
