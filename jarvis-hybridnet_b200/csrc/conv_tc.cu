@@ -421,50 +421,77 @@ int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st
 }
 
 // InstanceNorm (from the fused sum / sum-of-squares) [+ residual] [ReLU] [+ skip], in place on a BP tensor;
-// optionally also writes the parity-split copy the following stride-2 convolution reads.
-__global__ void __launch_bounds__(256)
+// optionally also writes the parity-split copy the following stride-2 convolution reads.  HBM-bound: one block
+// per (sample, 8-channel chunk, z-plane) walks the plane's contiguous run of padded positions with 16-byte
+// accesses; the 8 (mean, rstd) pairs are computed once per block, pad columns are skipped (they stay zero).
+constexpr int NORM_THREADS = 256, NORM_UNROLL = 3;
+template <bool HAS_RES, bool HAS_POST, bool HAS_PS>
+__global__ void __launch_bounds__(NORM_THREADS)
 tc_norm_act_kernel(uint4 *__restrict__ x, const float *__restrict__ stats, const uint4 *__restrict__ residual,
                    const uint4 *__restrict__ post_add, uint4 *__restrict__ ps_out, int relu, int D, int CJ, int NOUT,
-                   float inv_count, float eps)
+                   float inv_count, float eps, uint32_t wp_magic)
 {
-    const int nv = D * D * D;
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nv) return;
-    const int bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
-    const int z = v / (D * D), r = v - z * D * D, y = r / D, xq = r - y * D;
-    const int Wp = D + 2;
-    const size_t o = (((size_t)bj * Wp + z + 1) * Wp + y + 1) * Wp + xq + 1;
-    const uint4 raw = x[o];
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    uint32_t rs[4] = {0, 0, 0, 0}, pa[4] = {0, 0, 0, 0};
-    if (residual) { const uint4 t = residual[o]; rs[0] = t.x; rs[1] = t.y; rs[2] = t.z; rs[3] = t.w; }
-    if (post_add) { const uint4 t = post_add[o]; pa[0] = t.x; pa[1] = t.y; pa[2] = t.z; pa[3] = t.w; }
-    uint32_t outw[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float f[2] = {__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u)};
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int c = j * 8 + 2 * i + e;
-            const float sum = stats[((size_t)b * NOUT + c) * 2], sq = stats[((size_t)b * NOUT + c) * 2 + 1];
-            const float mean = sum * inv_count;
-            const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
-            float yv = (f[e] - mean) * rsqrtf(var + eps);
-            if (residual) yv += e ? __uint_as_float(rs[i] & 0xffff0000u) : __uint_as_float(rs[i] << 16);
-            if (relu) yv = fmaxf(yv, 0.f);
-            if (post_add) yv += e ? __uint_as_float(pa[i] & 0xffff0000u) : __uint_as_float(pa[i] << 16);
-            f[e] = yv;
-        }
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[0], f[1]);
-        outw[i] = *reinterpret_cast<uint32_t *>(&h2);
+    __shared__ float sc[16];                                          // mean[8], rstd[8]
+    const int z = blockIdx.x, bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
+    const int Wp = D + 2, PP = Wp * Wp;
+    if (threadIdx.x < 8) {
+        const int c = j * 8 + threadIdx.x;
+        const float sum = stats[((size_t)b * NOUT + c) * 2], sq = stats[((size_t)b * NOUT + c) * 2 + 1];
+        const float mean = sum * inv_count;
+        const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
+        sc[threadIdx.x] = mean;
+        sc[8 + threadIdx.x] = rsqrtf(var + eps);
     }
-    const uint4 res = make_uint4(outw[0], outw[1], outw[2], outw[3]);
-    x[o] = res;
-    if (ps_out) {                                                     // [b][s][j][zp][pp] on the D/2 grid
-        const int Dh = D / 2, Wh = Dh + 2;
-        const int s = ((z & 1) * 2 + (y & 1)) * 2 + (xq & 1);
-        const size_t po = ((((size_t)b * 8 + s) * CJ + j) * Wh + (z >> 1) + 1) * Wh * Wh + (size_t)((y >> 1) + 1) * Wh + (xq >> 1) + 1;
-        ps_out[po] = res;
+    __syncthreads();
+    float mean[8], rstd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mean[i] = sc[i]; rstd[i] = sc[8 + i]; }
+    const size_t plane = ((size_t)bj * Wp + z + 1) * PP;
+    const int p_begin = Wp + 1, p_end = D * Wp + D + 1;               // first / one-past-last interior position
+    const int Dh = D / 2, Wh = Dh + 2;
+    for (int p0 = p_begin + threadIdx.x; p0 < p_end; p0 += NORM_THREADS * NORM_UNROLL) {
+        uint4 raw[NORM_UNROLL], rs[NORM_UNROLL], pa[NORM_UNROLL];
+        bool ok[NORM_UNROLL];
+        int yp[NORM_UNROLL], xp[NORM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < NORM_UNROLL; ++u) {
+            const int p = p0 + u * NORM_THREADS;
+            yp[u] = (int)__umulhi((uint32_t)p, wp_magic);             // p / Wp (exact for p * Wp < 2^32)
+            xp[u] = p - yp[u] * Wp;
+            ok[u] = p < p_end && xp[u] >= 1 && xp[u] <= D;
+            if (ok[u]) {
+                raw[u] = x[plane + p];
+                if (HAS_RES) rs[u] = residual[plane + p];
+                if (HAS_POST) pa[u] = post_add[plane + p];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NORM_UNROLL; ++u) {
+            if (!ok[u]) continue;
+            const int p = p0 + u * NORM_THREADS;
+            const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+            const uint32_t rw[4] = {rs[u].x, rs[u].y, rs[u].z, rs[u].w};
+            const uint32_t pw[4] = {pa[u].x, pa[u].y, pa[u].z, pa[u].w};
+            uint32_t outw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float f0 = (__uint_as_float(w[i] << 16) - mean[2 * i]) * rstd[2 * i];
+                float f1 = (__uint_as_float(w[i] & 0xffff0000u) - mean[2 * i + 1]) * rstd[2 * i + 1];
+                if (HAS_RES) { f0 += __uint_as_float(rw[i] << 16); f1 += __uint_as_float(rw[i] & 0xffff0000u); }
+                if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                if (HAS_POST) { f0 += __uint_as_float(pw[i] << 16); f1 += __uint_as_float(pw[i] & 0xffff0000u); }
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                outw[i] = *reinterpret_cast<uint32_t *>(&h2);
+            }
+            const uint4 res = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+            x[plane + p] = res;
+            if (HAS_PS) {                                              // [b][s][j][zp][pp] on the D/2 grid
+                const int y = yp[u] - 1, xq = xp[u] - 1;
+                const int s = ((z & 1) * 2 + (y & 1)) * 2 + (xq & 1);
+                const size_t po = ((((size_t)b * 8 + s) * CJ + j) * Wh + (z >> 1) + 1) * Wh * Wh + (size_t)((y >> 1) + 1) * Wh + (xq >> 1) + 1;
+                ps_out[po] = res;
+            }
+        }
     }
 }
 
@@ -773,10 +800,20 @@ struct TcCtx {
     int norm(uint4 *x, const float *stats, int l, int D, const uint4 *residual, bool relu, const uint4 *post_add, uint4 *ps) const
     {
         const TcLayer &T = net->tc->layer[l];
-        const int nv = D * D * D, CJ = T.cout_pad / 8;
-        JHN_LAUNCH("tc_norm_act_kernel", st,
-                   tc_norm_act_kernel<<<dim3(cdiv(nv, 256), B * CJ), 256, 0, st>>>(x, stats, residual, post_add, ps, relu ? 1 : 0, D, CJ,
-                                                                                  T.cout_pad, 1.f / (float)nv, 1e-5f));
+        const int nv = D * D * D, CJ = T.cout_pad / 8, Wp = D + 2;
+        const uint32_t magic = (uint32_t)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);   // ceil(2^32 / Wp)
+        const dim3 grid(D, B * CJ);
+        const float inv = 1.f / (float)nv;
+#define JHN_NORM(R, P, S)                                                                                              \
+        JHN_LAUNCH("tc_norm_act_kernel", st,                                                                           \
+                   (tc_norm_act_kernel<R, P, S><<<grid, NORM_THREADS, 0, st>>>(x, stats, residual, post_add, ps, relu ? 1 : 0, D, CJ, \
+                                                                               T.cout_pad, inv, 1e-5f, magic)))
+        if (residual && post_add && !ps) JHN_NORM(true, true, false);
+        else if (residual && !post_add && ps) JHN_NORM(true, false, true);
+        else if (residual && !post_add && !ps) JHN_NORM(true, false, false);
+        else if (!residual && !post_add && !ps) JHN_NORM(false, false, false);
+        else return fail(JHN_ERR_ARG, "norm: unsupported operand combination");
+#undef JHN_NORM
         return JHN_OK;
     }
     int zero_border(uint4 *t, int chunks_total, int D) const { return tc_zero_border_launch(t, chunks_total, D, st); }
