@@ -61,7 +61,8 @@ int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st);
 void tc_destroy(jhn_v2v *net);
 size_t tc_workspace(const jhn_v2v *net, int B, int G);
 int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws,
-               size_t ws_bytes, cudaStream_t st);
+               size_t ws_bytes, cudaStream_t st, const TailArgs *tail);
+bool head_supported(int K, int cin_pad, int cout_pad, int D);
 
 int tc_debug_layer(const jhn_v2v *net, int l, const float *in, int B, int D, float *out, void *ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_debug_workspace(const jhn_v2v *net, int l, int B, int D);
@@ -211,7 +212,7 @@ int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, in
         if (in_layout != JHN_VOL_NCDHW_F32) return fail(JHN_ERR_ARG, "fp32 V2V takes the NCDHW fp32 volume");
         return v2v_f32_forward(net, (const float *)volume_in, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream);
     }
-    return tc_forward(net, volume_in, in_layout, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream);
+    return tc_forward(net, volume_in, in_layout, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
 }
 
 int jhn_v2v_debug_layer_workspace_bytes(const jhn_v2v *net, int layer, int B, int D, size_t *bytes)
@@ -285,6 +286,13 @@ int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps
         net->zv_ptr = vol; net->zv_B = B; net->zv_G = G;
     }
     JHN_TRY(reproject_launch(ra, ws_r, rws, (cudaStream_t)stream));
+    const int c2 = (2 * net->K + 15) / 16 * 16, c1 = (net->K + 15) / 16 * 16;
+    if (net->precision == JHN_BF16 && head_supported(net->K, c2, c1, h) &&
+        head_acc_bytes(B, net->K) <= (size_t)B * net->K * h * h * h * sizeof(float)) {
+        // bf16 path: the output layer's epilogue is the centroid tail; the [B,K,h^3] volume is never materialised
+        TailArgs tail{spacing, roi, center3D, points, conf, argmax, vout};
+        return tc_forward(net, vol, hybrid_layout(net), B, G, nullptr, ws_v, align_up(v2v, 256), (cudaStream_t)stream, &tail);
+    }
     JHN_TRY(jhn_v2v_forward(net, vol, hybrid_layout(net), B, G, vout, ws_v, align_up(v2v, 256), stream));
     return jhn_centroid_reduce(vout, B, net->K, h, spacing, roi, center3D, points, conf, argmax, stream);
 }

@@ -820,8 +820,14 @@ struct TcCtx {
 };
 }  // namespace
 
+bool head_supported(int K, int cin_pad, int cout_pad, int D);
+int head_centroid_launch(const void *in, const __nv_bfloat16 *w, const float *bias, int B, int D, int K, int cin_pad, int cout_pad,
+                         float spacing, float roi, const int32_t *center3D, float *points, float *conf, int32_t *argmax, void *acc,
+                         int sms, int max_smem, cudaStream_t st);
+
+// `tail` non-null: the output layer runs fused with the centroid tail and `out` is not written (may be null).
 int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws, size_t ws_bytes,
-               cudaStream_t st)
+               cudaStream_t st, const TailArgs *tail)
 {
     const TcNet *tc = net->tc;
     if (!tc) return fail(JHN_ERR_ARG, "network was not created with JHN_BF16");
@@ -882,6 +888,11 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
     JHN_TRY(c.norm(t.Dd, S(9), L_DECA, h, nullptr, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_DECB, t.Dd, j2, h, t.E, j2, S(10)));
     JHN_TRY(c.norm(t.E, S(10), L_DECB, h, t.A, true, t.Bq, nullptr));                 // relu(.. + x) + skip   :81
+    if (tail) {                                                                        // output_layer + model.py:73-87
+        const TcLayer &H = tc->layer[L_HEAD];
+        return head_centroid_launch(t.E, H.w, H.bias, B, h, net->K, H.cin_pad, H.cout_pad, tail->spacing, tail->roi, tail->center3D,
+                                    tail->points, tail->conf, tail->argmax, tail->acc, sms, tc->max_smem, st);
+    }
     return c.conv(L_HEAD, t.E, j2, h, out, 0, nullptr);                               // output_layer     v2vnet.py:101
 }
 

@@ -35,6 +35,15 @@ struct jhn_v2v {
 };
 
 namespace jhn {
+// centroid tail fused into the bf16 output layer (head_tc.cu); `acc` is head_acc_bytes(B, K) of scratch
+struct TailArgs {
+    float spacing, roi;
+    const int32_t *center3D;
+    float *points, *conf;
+    int32_t *argmax;
+    void *acc;
+};
+size_t head_acc_bytes(int B, int K);
 void layer_table(int K, LayerDesc *d);
 size_t v2v_f32_workspace(const jhn_v2v *net, int B, int G);
 int v2v_f32_forward(const jhn_v2v *net, const float *x, int B, int G, float *out, void *ws, size_t ws_bytes,
