@@ -298,36 +298,53 @@ def main():
     pk = peaks()
     fl = v2v_flops(sh)
     kern = {k: dict(launches=n, ms_per_step=msk / K_steps) for k, (n, msk) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-    s_in = 4
-    rp_ms = sum(v["ms_per_step"] for k, v in kern.items() if k in ("coarse_project_kernel", "fine_index_kernel",
-                                                                   "relayout_kernel", "gather_mean_kernel"))
+    s_in, s_vol = 4, (4 if precision == "fp32" else 2)
+    REPRO = ("coarse_project_kernel", "fine_index_kernel", "relayout_kernel", "gather_mean_kernel", "gather_fused_kernel",
+             "gather_staged_kernel")
+    rp_ms = sum(v["ms_per_step"] for k, v in kern.items() if k in REPRO)
     conv_ms = sum(v["ms_per_step"] for k, v in kern.items() if "conv" in k)
     tail_ms = sum(v["ms_per_step"] for k, v in kern.items() if "centroid" in k)
     stages = dict(
-        reproject=dict(ms_per_step=rp_ms, algorithmic_GB_per_s=B * repro_bytes(sh, s_in, 4 if precision == "fp32" else 2) / (rp_ms * 1e-3) / 1e9 if rp_ms else None),
-        v2v_convs=dict(ms_per_step=conv_ms, algorithmic_TFLOP_per_s=B * fl["total"] / (conv_ms * 1e-3) / 1e12 if conv_ms else None),
-        tail=dict(ms_per_step=tail_ms, algorithmic_GB_per_s=B * sh.K * sh.h ** 3 * 4 / (tail_ms * 1e-3) / 1e9 if tail_ms else None),
+        reproject=dict(ms_per_step=rp_ms, algorithmic_GB_per_s=B * repro_bytes(sh, s_in, s_vol) / (rp_ms * 1e-3) / 1e9 if rp_ms else None),
+        v2v_convs=dict(ms_per_step=conv_ms, algorithmic_TFLOP_per_s=B * fl["total"] / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
+                       note="includes the fused output-layer + centroid kernel on the bf16 path"),
+        tail=dict(ms_per_step=tail_ms),
     )
-    top = next(iter(kern)) if kern else None
-    roofline = None
-    if top is not None:
-        per_launch_ms = prof[top][1] / prof[top][0]
-        if "conv" in top or "tc_" in top:
-            fam = {"tc_conv_k3_resident": fl["res_k3_2C"], "tc_conv_k3_streamed": fl["res_k3_4C"],
-                   "tc_conv_front_k3s2": fl["front_k3s2"], "tc_conv_pool_k2s2": fl["pool_k2s2"],
-                   "tc_conv_up_convT": fl["up_convT"], "tc_conv_head_1x1": fl["head_1x1"],
-                   "conv3d_f32_kernel<3>": fl["front_k3s2"] + fl["res_k3_2C"] + fl["res_k3_4C"]}
-            per_step = fam.get(top, fl["total"])
-            n_per_step = prof[top][0] / K_steps
-            ach = B * per_step / n_per_step / (per_launch_ms * 1e-3) / 1e12
-            roofline = dict(kernel=top, bound="tensor", achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
-                            frac=ach / pk["bf16_sustained"], traffic=None, peak_source=pk["src"] + ", sustained bf16",
-                            algorithmic_flop_per_launch=B * per_step / n_per_step, avg_launch_ms=per_launch_ms)
-        else:
-            byts = B * repro_bytes(sh, s_in, 4 if precision == "fp32" else 2)
-            ach = byts / (per_launch_ms * 1e-3) / 1e9
-            roofline = dict(kernel=top, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
-                            traffic=None, peak_source=pk["src"], algorithmic_bytes_per_launch=byts, avg_launch_ms=per_launch_ms)
+    # algorithmic work per STEP of each kernel family: FLOP for the GEMM kernels, bytes for the rest
+    act = lambda c, d: B * c * d ** 3 * 2                                    # one bf16 activation tensor, un-padded
+    h, q, K = sh.h, sh.h // 2, sh.K
+    flop_fam = {"tc_conv3_stacked": fl["res_k3_2C"], "tc_conv_k3_resident": fl["res_k3_2C"], "tc_conv_k3_streamed": fl["res_k3_4C"],
+                "tc_conv_front_k3s2": fl["front_k3s2"], "tc_conv_pool_k2s2": fl["pool_k2s2"], "tc_conv_up_convT": fl["up_convT"],
+                "tc_conv_head_1x1": fl["head_1x1"], "conv3d_f32_kernel<3>": fl["front_k3s2"] + fl["res_k3_2C"] + fl["res_k3_4C"]}
+    byte_fam = {"gather_staged_kernel": B * repro_bytes(sh, 2, s_vol), "gather_fused_kernel": B * repro_bytes(sh, s_vol, s_vol),
+                "gather_mean_kernel": B * repro_bytes(sh, s_vol, s_vol),
+                "relayout_kernel": B * sh.ncam * K * sh.hm ** 2 * (s_in + s_vol),
+                "coarse_project_kernel": B * sh.ncam * h ** 3 * 8,
+                "tc_head_centroid_kernel": act(2 * K, h), "centroid_kernel": B * K * h ** 3 * 4,
+                # 7 plain + 1 residual + 1 residual/PS-copy + 1 residual/skip on the h grid, 2 plain + 1 residual on the q grid
+                "tc_norm_act_kernel": (7 * 2 + 3 + 4 + 4) * act(2 * K, h) + (2 * 2 + 3) * act(4 * K, q)}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")                 # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp) and args.workload == "c3_full3d_example" and B == 32:
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch", {})
+    rooflines = {}
+    for k, v in kern.items():
+        n_per_step = prof[k][0] / K_steps
+        per_launch_ms = prof[k][1] / prof[k][0]
+        if k in flop_fam:
+            work = B * flop_fam[k] / n_per_step
+            ach = work / (per_launch_ms * 1e-3) / 1e12
+            rooflines[k] = dict(kernel=k, bound="tensor", achieved=ach, peak=pk["bf16_sustained"], unit="TFLOP/s",
+                                frac=ach / pk["bf16_sustained"], traffic=traffic.get(k), peak_source=pk["src"] + ", sustained bf16",
+                                algorithmic_flop_per_launch=work, avg_launch_ms=per_launch_ms)
+        elif k in byte_fam:
+            work = byte_fam[k] / n_per_step
+            ach = work / (per_launch_ms * 1e-3) / 1e9
+            rooflines[k] = dict(kernel=k, bound="hbm", achieved=ach, peak=pk["hbm"], unit="GB/s", frac=ach / pk["hbm"],
+                                traffic=traffic.get(k), peak_source=pk["src"], algorithmic_bytes_per_launch=work,
+                                avg_launch_ms=per_launch_ms)
+    top = next(iter(kern)) if kern else None                                # dominant kernel = most device time per step
+    roofline = rooflines.get(top)
 
     if rank == 0:
         cb = None if args.no_cpu_baseline or world > 1 else cpu_baseline(sh)
@@ -339,7 +356,7 @@ def main():
                                 l2="inputs rotate through %d batches of %.0f MB (>> 126 MB L2)" % (n_pool, B * sh.ncam * sh.K * sh.hm ** 2 * 4 / 1e6),
                                 timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded"),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb,
-                    stages=stages, kernels=kern, gather_ms=gather_ms)
+                    stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
