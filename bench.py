@@ -213,6 +213,8 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 under torch.distributed.run")
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"               # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sh, B = wl["shape"], wl["batch"]
