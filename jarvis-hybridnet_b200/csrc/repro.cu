@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256)
 coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ intr,
                       const float *__restrict__ dist, const int32_t *__restrict__ center3D,
                       const int32_t *__restrict__ centerHM, int B, int ncam, int h, float spacing, int hs,
-                      float *__restrict__ ca, float *__restrict__ cb)
+                      float2 *__restrict__ cab)
 {
     extern __shared__ float cp[];                       // [ncam][CP_PARAMS]
     const int b = blockIdx.y;
@@ -100,8 +100,7 @@ coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ i
         bb = fminf(fmaxf(bb, loy), hiy);                                                      // :67-68
         bb = __fsub_rn(__fadd_rn(__fsub_rn(bb, chy), fhs), 1.f);
         const size_t o = ((size_t)b * ncam + c) * nc + t;
-        ca[o] = a;
-        cb[o] = bb;
+        cab[o] = make_float2(a, bb);                         // (x, y) interleaved: one 8-byte access per corner downstream
     }
 }
 
@@ -220,7 +219,7 @@ constexpr int CS = TS / 2 + 2;                          // coarse corners per di
 // One CTA = one TS^3 tile of fine voxels of frame set blockIdx.y.
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(256)
-gather_fused_kernel(const T *__restrict__ hm, const float *__restrict__ ca, const float *__restrict__ cb, int ncam, int K,
+gather_fused_kernel(const T *__restrict__ hm, const float2 *__restrict__ cab, int ncam, int K,
                     int hs, int G, int lerp_mode, float post_divide, void *__restrict__ out_, int32_t *__restrict__ idx_out)
 {
     extern __shared__ __align__(16) uint8_t gsm[];
@@ -239,8 +238,9 @@ gather_fused_kernel(const T *__restrict__ hm, const float *__restrict__ ca, cons
                   gk = min(max(K0 / 2 - 1 + lk, 0), h - 1);
         const size_t o = ((size_t)b * ncam + c) * nc + ((size_t)gi * h + gj) * h + gk;
         const int l = (li * CS + lj) * CS + lk;
-        co[(c * 2 + 0) * CS * CS * CS + l] = __ldg(ca + o);
-        co[(c * 2 + 1) * CS * CS * CS + l] = __ldg(cb + o);
+        const float2 ab = __ldg(cab + o);
+        co[(c * 2 + 0) * CS * CS * CS + l] = ab.x;
+        co[(c * 2 + 1) * CS * CS * CS + l] = ab.y;
     }
     __syncthreads();
 
@@ -388,21 +388,44 @@ constexpr int G_STAGES = JHN_G_STAGES, G_THREADS = 160;
 constexpr int G_PIX_BYTES = KP * 2;                                           // 48 B per staged pixel
 constexpr int G_CAM_FLOATS = 2 * GC3 + 6;                                     // per camera: corners a / b, then x0 y0 bw bh|0 pitch
 
-template <int MODE> __device__ __forceinline__ float lerp_t(float w0, float a, float w1, float b)
+// Packed fp32x2 arithmetic (sm_100 FMUL2 / FFMA2 / FADD2): the x and the y pixel coordinate of a corner travel
+// as one 64-bit register pair through the three nested lerps, each half an IEEE round-to-nearest fp32
+// operation exactly like the scalar instruction — half the issue slots of the index chain.
+__device__ __forceinline__ uint64_t f2_pack(float x, float y)
 {
-    if (MODE == JHN_LERP_FMA_FIRST) return __fmaf_rn(w0, a, __fmul_rn(w1, b));
-    if (MODE == JHN_LERP_FMA_SECOND) return __fmaf_rn(w1, b, __fmul_rn(w0, a));
-    return __fadd_rn(__fmul_rn(w0, a), __fmul_rn(w1, b));
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &x, float &y)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b)
+{
+    uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+template <int MODE> __device__ __forceinline__ uint64_t lerp2(uint64_t w0, uint64_t a, uint64_t w1, uint64_t b)
+{
+    if (MODE == JHN_LERP_FMA_FIRST) return f2_fma(w0, a, f2_mul(w1, b));
+    if (MODE == JHN_LERP_FMA_SECOND) return f2_fma(w1, b, f2_mul(w0, a));
+    return f2_add(f2_mul(w0, a), f2_mul(w1, b));
 }
 
 template <int LAYOUT, int MODE>
 __global__ void __launch_bounds__(G_THREADS, JHN_G_MINBLOCKS)
-gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca, const float *__restrict__ cb, int ncam,
+gather_staged_kernel(const __half *__restrict__ hm, const float2 *__restrict__ cab, int ncam,
                      int K, int hs, int G, float post_scale, int cap_bytes, void *__restrict__ out_)
 {
     extern __shared__ __align__(128) uint8_t gsm[];
     uint8_t *ring = gsm;                                                       // [G_STAGES][cap_bytes] pixel boxes
-    float *cams = reinterpret_cast<float *>(gsm + (size_t)G_STAGES * cap_bytes);   // [ncam][G_CAM_FLOATS]
+    float *cams = reinterpret_cast<float *>(gsm + (size_t)G_STAGES * cap_bytes);   // [ncam][G_CAM_FLOATS]: corners (x, y), box
     uint64_t *bars = reinterpret_cast<uint64_t *>(cams + (size_t)ncam * G_CAM_FLOATS);
     uint64_t *full = bars, *empty = bars + G_STAGES;
     const int h = G / 2, nt = G / GT + 1;
@@ -415,42 +438,50 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
         for (int i = 0; i < G_STAGES; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // ---- the tile's 5^3 coarse corners of every camera -> smem (indices clamped to the grid, like ATen's reads)
-    for (int e = threadIdx.x; e < ncam * GC3; e += G_THREADS) {
-        const int c = e / GC3, l = e - c * GC3;
-        const int lk = l % GC, lj = (l / GC) % GC, li = l / (GC * GC);
-        const int gi = min(max(GCELL * ti - 1 + li, 0), h - 1), gj = min(max(GCELL * tj - 1 + lj, 0), h - 1),
-                  gk = min(max(GCELL * tk - 1 + lk, 0), h - 1);
-        const size_t o = ((size_t)b * ncam + c) * nc + ((size_t)gi * h + gj) * h + gk;
-        cams[c * G_CAM_FLOATS + l] = __ldg(ca + o);
-        cams[c * G_CAM_FLOATS + GC3 + l] = __ldg(cb + o);
-    }
-    __syncthreads();
-    // ---- per camera: pixel box bounding every index of the tile (one warp per camera, round robin)
-    for (int c = warp; c < ncam; c += G_THREADS / 32) {
-        const float *A = cams + c * G_CAM_FLOATS;
-        float amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
-        for (int l = lane; l < GC3; l += 32) {
-            const float a = A[l], bb = A[GC3 + l];
-            amin = fminf(amin, a); amax = fmaxf(amax, a); bmin = fminf(bmin, bb); bmax = fmaxf(bmax, bb);
-        }
+    // ---- one warp per camera (round robin): the tile's 5^3 coarse corners -> smem (grid indices clamped, like
+    // ATen's reads) and, in the same pass, their min / max -> the pixel box bounding every index of the tile
+    {
+        int go[4];                                                             // this lane's <= 4 corners: offset in the coarse grid
 #pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1) {
-            amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, sh)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, sh));
-            bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, sh)); bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, sh));
+        for (int r = 0; r < 4; ++r) {
+            const int l = min(lane + 32 * r, GC3 - 1);
+            const int lk = l % GC, lj = (l / GC) % GC, li = l / (GC * GC);
+            const int gi = min(max(GCELL * ti - 1 + li, 0), h - 1), gj = min(max(GCELL * tj - 1 + lj, 0), h - 1),
+                      gk = min(max(GCELL * tk - 1 + lk, 0), h - 1);
+            go[r] = (gi * h + gj) * h + gk;
         }
-        if (lane == 0) {
-            const int x0 = __float2int_rz(__fmul_rn(amin, 0.5f)), x1 = __float2int_rz(__fmul_rn(amax, 0.5f));
-            const int y0 = __float2int_rz(__fmul_rn(bmin, 0.5f)), y1 = __float2int_rz(__fmul_rn(bmax, 0.5f));
-            const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-            // smem row pitch in pixels, == 3 or 5 (mod 8): a pixel vector is three 16-byte bank groups, so two
-            // pixels collide iff their linear offsets differ by a multiple of 8; with such a pitch the short
-            // pixel runs a quarter-warp (8 voxels along z) touches almost never do
-            int pitch = bw;
-            while ((pitch & 7) != 3 && (pitch & 7) != 5) ++pitch;
-            const bool fits = pitch * bh * G_PIX_BYTES <= cap_bytes && x0 >= 0 && y0 >= 0 && x1 < hs && y1 < hs;
-            int *mi = reinterpret_cast<int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-            mi[0] = x0; mi[1] = y0; mi[2] = bw; mi[3] = fits ? bh : 0; mi[4] = pitch;
+        for (int c = warp; c < ncam; c += G_THREADS / 32) {
+            const float2 *src = cab + ((size_t)b * ncam + c) * nc;
+            float2 *dst = reinterpret_cast<float2 *>(cams + c * G_CAM_FLOATS);
+            float2 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = __ldg(src + go[r]);
+            float amin = v[0].x, amax = v[0].x, bmin = v[0].y, bmax = v[0].y;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (lane + 32 * r < GC3) dst[lane + 32 * r] = v[r];
+                amin = fminf(amin, v[r].x); amax = fmaxf(amax, v[r].x); bmin = fminf(bmin, v[r].y); bmax = fmaxf(bmax, v[r].y);
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, sh)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, sh));
+                bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, sh)); bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, sh));
+            }
+            if (lane == 0) {
+                const int x0 = __float2int_rz(__fmul_rn(amin, 0.5f)), x1 = __float2int_rz(__fmul_rn(amax, 0.5f));
+                const int y0 = __float2int_rz(__fmul_rn(bmin, 0.5f)), y1 = __float2int_rz(__fmul_rn(bmax, 0.5f));
+                const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+                // smem row pitch in pixels, == 3 or 5 (mod 8): a pixel vector is three 16-byte bank groups, so two
+                // pixels collide iff their linear offsets differ by a multiple of 8; with such a pitch the short
+                // pixel runs a quarter-warp (8 voxels along z) touches almost never do
+                int pitch = bw;
+                while ((pitch & 7) != 3 && (pitch & 7) != 5) ++pitch;
+                const bool fits = pitch * bh * G_PIX_BYTES <= cap_bytes && x0 >= 0 && y0 >= 0 && x1 < hs && y1 < hs;
+                int *mi = reinterpret_cast<int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
+                // byte offset of pixel (px, py): py * mi[4] + px * 48 + mi[5], inside the staged box or (box too large) the whole map
+                mi[0] = x0; mi[1] = y0; mi[2] = bw; mi[3] = fits ? bh : 0;
+                mi[4] = (fits ? pitch : hs) * G_PIX_BYTES; mi[5] = fits ? -(y0 * pitch + x0) * G_PIX_BYTES : 0;
+            }
         }
     }
     __syncthreads();
@@ -461,7 +492,7 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
             const int s = c % G_STAGES;
             if (c >= G_STAGES) mbar_wait(smem_u32(empty + s), (uint32_t)((c / G_STAGES) - 1) & 1u);
             const int *mi = reinterpret_cast<const int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-            const int x0 = mi[0], y0 = mi[1], bw = mi[2], bh = mi[3], pitch = mi[4];
+            const int x0 = mi[0], y0 = mi[1], bw = mi[2], bh = mi[3], rowB = mi[4];
             const uint32_t fb = smem_u32(full + s);
             if (bh == 0) {                                                     // box does not fit: gathered from global memory
                 if (lane == 0) mbar_arrive(fb);
@@ -473,7 +504,7 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
             uint8_t *box = ring + (size_t)s * cap_bytes;
             const uint8_t *src = reinterpret_cast<const uint8_t *>(hm) + ((((size_t)b * ncam + c) * hs + y0) * hs + x0) * G_PIX_BYTES;
             for (int r = lane; r < bh; r += 32)
-                bulk_load(smem_u32(box + (size_t)r * pitch * G_PIX_BYTES), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
+                bulk_load(smem_u32(box + (size_t)r * rowB), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
         }
         return;
     }
@@ -483,11 +514,13 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
     const int I0 = GT * ti - 1 + 2 * ci, J0 = GT * tj - 1 + 2 * cj, Kz = GT * tk - 1 + 2 * ck + kv;
     // ATen area_pixel_compute_source_index, scale .5: odd fine index -> lambda1 .25, even -> .75, index 0 -> 0
     const float lk1 = Kz == 0 ? 0.f : (kv ? 0.75f : 0.25f), lk0 = __fsub_rn(1.f, lk1);
-    float lj1[2], lj0[2], li1[2], li0[2];
+    const uint64_t wk0 = f2_pack(lk0, lk0), wk1 = f2_pack(lk1, lk1), whalf = f2_pack(0.5f, 0.5f);
+    uint64_t wj1[2], wj0[2], wi1[2], wi0[2];
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
-        lj1[v] = (J0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f); lj0[v] = __fsub_rn(1.f, lj1[v]);
-        li1[v] = (I0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f); li0[v] = __fsub_rn(1.f, li1[v]);
+        const float j1 = (J0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f), j0 = __fsub_rn(1.f, j1);
+        const float i1 = (I0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f), i0 = __fsub_rn(1.f, i1);
+        wj1[v] = f2_pack(j1, j1); wj0[v] = f2_pack(j0, j0); wi1[v] = f2_pack(i1, i1); wi0[v] = f2_pack(i0, i0);
     }
     __half2 acc[4][KP / 2];
 #pragma unroll
@@ -498,35 +531,30 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
 
     for (int c = 0; c < ncam; ++c) {
         const int s = c % G_STAGES;
-        const float *A = cams + c * G_CAM_FLOATS + l0, *Bc = A + GC3;
+        const uint64_t *Cn = reinterpret_cast<const uint64_t *>(cams + c * G_CAM_FLOATS) + l0;      // (x, y) corner pairs
         const int *mi = reinterpret_cast<const int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-        const int x0 = mi[0], y0 = mi[1], fits = mi[3], bw = mi[4];                  // bw: smem row pitch from here on
+        const int fits = mi[3], rowB = mi[4], baseB = mi[5];
         // indices of this thread's four voxels (registers only; same arithmetic as gather_fused_kernel phase A)
-        float xa[2][2], xb[2][2];
+        uint64_t xk[2][2];
 #pragma unroll
         for (int p = 0; p < 2; ++p)
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int l = (p * GC + q) * GC;
-                xa[p][q] = lerp_t<MODE>(lk0, A[l], lk1, A[l + 1]);
-                xb[p][q] = lerp_t<MODE>(lk0, Bc[l], lk1, Bc[l + 1]);
+                xk[p][q] = lerp2<MODE>(wk0, Cn[l], wk1, Cn[l + 1]);
             }
         int off[4];
 #pragma unroll
         for (int jv = 0; jv < 2; ++jv) {
-            float ya[2], yb[2];
+            uint64_t yj[2];
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                ya[p] = lerp_t<MODE>(lj0[jv], xa[p][0], lj1[jv], xa[p][1]);
-                yb[p] = lerp_t<MODE>(lj0[jv], xb[p][0], lj1[jv], xb[p][1]);
-            }
+            for (int p = 0; p < 2; ++p) yj[p] = lerp2<MODE>(wj0[jv], xk[p][0], wj1[jv], xk[p][1]);
 #pragma unroll
             for (int iv = 0; iv < 2; ++iv) {
-                const float fa = lerp_t<MODE>(li0[iv], ya[0], li1[iv], ya[1]);
-                const float fb2 = lerp_t<MODE>(li0[iv], yb[0], li1[iv], yb[1]);
-                const int px = __float2int_rz(__fmul_rn(fa, 0.5f));                      // (val/2).int()   repro_layer.py:82-83
-                const int py = __float2int_rz(__fmul_rn(fb2, 0.5f));
-                off[iv * 2 + jv] = fits ? ((py - y0) * bw + (px - x0)) * G_PIX_BYTES : (py * hs + px) * G_PIX_BYTES;
+                float fa, fb2;
+                f2_unpack(f2_mul(lerp2<MODE>(wi0[iv], yj[0], wi1[iv], yj[1]), whalf), fa, fb2);
+                const int px = __float2int_rz(fa), py = __float2int_rz(fb2);                        // (val/2).int()   repro_layer.py:82-83
+                off[iv * 2 + jv] = py * rowB + (px * G_PIX_BYTES + baseB);
             }
         }
         mbar_wait(smem_u32(full + s), (uint32_t)(c / G_STAGES) & 1u);
@@ -600,7 +628,7 @@ gather_staged_kernel(const __half *__restrict__ hm, const float *__restrict__ ca
 }
 
 template <int LAYOUT>
-static int launch_staged(const ReprojectArgs &a, const __half *hm_cl, const float *ca, const float *cb, int cap, cudaStream_t st)
+static int launch_staged(const ReprojectArgs &a, const __half *hm_cl, const float2 *cab, int cap, cudaStream_t st)
 {
     const size_t gsmem = (size_t)G_STAGES * cap + (size_t)a.ncam * G_CAM_FLOATS * 4 + 2 * G_STAGES * 8;
     if (gsmem > 200 * 1024) return fail(JHN_ERR_SHAPE, "too many cameras (%d) for the staged gather", a.ncam);
@@ -613,7 +641,7 @@ static int launch_staged(const ReprojectArgs &a, const __half *hm_cl, const floa
         auto kern = gather_staged_kernel<LAYOUT, MODE>;                                                          \
         JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));           \
         JHN_LAUNCH("gather_staged_kernel", st,                                                                   \
-                   kern<<<grid, G_THREADS, gsmem, st>>>(hm_cl, ca, cb, a.ncam, a.K, a.hs, a.G, post_scale, cap, a.volume_out)); \
+                   kern<<<grid, G_THREADS, gsmem, st>>>(hm_cl, cab, a.ncam, a.K, a.hs, a.G, post_scale, cap, a.volume_out)); \
         return JHN_OK;                                                                                           \
     }
     if (a.lerp_mode == JHN_LERP_FMA_FIRST) JHN_STAGED(JHN_LERP_FMA_FIRST)
@@ -628,8 +656,7 @@ size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
 {
     const int h = G / 2;
     Arena a(nullptr, 0);
-    a.take<float>((size_t)B * ncam * h * h * h);                    // coarse a
-    a.take<float>((size_t)B * ncam * h * h * h);                    // coarse b
+    a.take<float2>((size_t)B * ncam * h * h * h);                   // coarse (x, y) pixel coordinates
     const size_t px = (size_t)B * ncam * hs * hs * KP;
     if (precision == JHN_FP32) a.take<float>(px); else a.take<__nv_bfloat16>(px);
     return a.off;
@@ -638,7 +665,7 @@ size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
 static size_t gather_smem(int ncam) { return (size_t)ncam * (2 * CS * CS * CS * sizeof(float) + TS * TS * TS * sizeof(int32_t)); }
 
 template <typename T>
-static int run_gather(const ReprojectArgs &a, const T *hm_cl, const float *ca, const float *cb, cudaStream_t st)
+static int run_gather(const ReprojectArgs &a, const T *hm_cl, const float2 *cab, cudaStream_t st)
 {
     const int nt = cdiv(a.G, TS);
     dim3 grid(nt * nt * nt, a.B);
@@ -648,7 +675,7 @@ static int run_gather(const ReprojectArgs &a, const T *hm_cl, const float *ca, c
         auto kern = gather_fused_kernel<T, JHN_VOL_NCDHW_F32>;
         JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         JHN_LAUNCH("gather_fused_kernel", st,
-                   kern<<<grid, 256, smem, st>>>(hm_cl, ca, cb, a.ncam, a.K, a.hs, a.G, a.lerp_mode, a.post_divide,
+                   kern<<<grid, 256, smem, st>>>(hm_cl, cab, a.ncam, a.K, a.hs, a.G, a.lerp_mode, a.post_divide,
                                                  a.volume_out, a.index_out));
         return JHN_OK;
     }
@@ -657,7 +684,7 @@ static int run_gather(const ReprojectArgs &a, const T *hm_cl, const float *ca, c
     auto kern = gather_fused_kernel<T, JHN_VOL_V2V_BF16>;
     JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     JHN_LAUNCH("gather_fused_kernel", st,
-               kern<<<grid, 256, smem, st>>>(hm_cl, ca, cb, a.ncam, a.K, a.hs, a.G, a.lerp_mode, a.post_divide,
+               kern<<<grid, 256, smem, st>>>(hm_cl, cab, a.ncam, a.K, a.hs, a.G, a.lerp_mode, a.post_divide,
                                              a.volume_out, a.index_out));
     return JHN_OK;
 }
@@ -666,30 +693,29 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
 {
     const int h = a.G / 2;
     Arena ar(ws, ws_bytes);
-    float *ca = ar.take<float>((size_t)a.B * a.ncam * h * h * h);
-    float *cb = ar.take<float>((size_t)a.B * a.ncam * h * h * h);
+    float2 *cab = ar.take<float2>((size_t)a.B * a.ncam * h * h * h);
     const size_t px = (size_t)a.B * a.ncam * a.hs * a.hs * KP;
     void *hm_cl = (a.precision == JHN_FP32) ? (void *)ar.take<float>(px) : (void *)ar.take<__nv_bfloat16>(px);
     if (!ar.ok()) return fail(JHN_ERR_WORKSPACE, "reproject workspace: need %zu bytes, got %zu", ar.off, ws_bytes);
 
     JHN_LAUNCH("coarse_project_kernel", st,
                coarse_project_kernel<<<dim3(cdiv((long long)h * h * h, 256), a.B), 256, a.ncam * CP_PARAMS * sizeof(float), st>>>(
-                   a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B, a.ncam, h, a.spacing, a.hs, ca, cb));
+                   a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B, a.ncam, h, a.spacing, a.hs, cab));
     if (a.precision == JHN_FP32) {
         JHN_TRY(launch_relayout<float>(a, (float *)hm_cl, st));
-        return run_gather<float>(a, (const float *)hm_cl, ca, cb, st);
+        return run_gather<float>(a, (const float *)hm_cl, cab, st);
     }
     if (!a.index_out && a.G % GT == 0) {
         // throughput path: fp16 staging copy + staged gather (the index dump needs the in-order kernel below)
         JHN_TRY(launch_relayout<__half>(a, (__half *)hm_cl, st));
         const int cap = pick_gather_cap(a.hs);
-        if (a.layout == JHN_VOL_NCDHW_F32) return launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, ca, cb, cap, st);
+        if (a.layout == JHN_VOL_NCDHW_F32) return launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, cap, st);
         const int CJ = (a.K + 15) / 16 * 2;
         if (!a.borders_valid) JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
-        return launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, ca, cb, cap, st);
+        return launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, cap, st);
     }
     JHN_TRY(launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)hm_cl, st));
-    return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, ca, cb, st);
+    return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, cab, st);
 }
 
 }  // namespace jhn
