@@ -23,6 +23,7 @@
 //                          cameras accumulated in order.  Writes NCDHW fp32 or the bf16 parity-split layout
 //                          of the first tensor-core convolution.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -627,6 +628,290 @@ gather_staged_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streaming gather: the staged gather as a persistent, software-pipelined kernel.  ncu of the one-tile-per-CTA
+// kernel above showed every CTA paying the chain  corner LDG -> box -> TMA -> first LDS  (~13 us per tile against
+// ~1 us of issue work), 27 % of the lanes parked on voxels outside the grid, and the LSU-shared pipe at 55 %.
+// Here a CTA walks tiles blockIdx.x, +gridDim.x, ... and the producer warp runs ahead of the gather warps across
+// tile boundaries through two rings: a deep one of small headers [150 (x, y) corner pairs | pixel box] and a
+// shallow one of pixel boxes.
+//   producer, item n:      wait header slot -> 150 x cp.async (LDGSTS, 8 B) corners into header n
+//             item n - D:  cp.async.wait_group -> own corners back -> integer min / max (REDUX) -> box -> wait box slot ->
+//                          mbarrier.arrive.expect_tx -> one cp.async.bulk per box row
+//   gather warps:          wait full -> corners + box meta -> indices -> LDS.128 -> HADD2 -> arrive both empties
+// z tiles are unshifted (6 corners along z instead of 5) so that no lane is ever outside the grid along z;
+// along x / y whole warps / quarter-warps outside the grid skip the step (no LSU wavefronts).
+// ------------------------------------------------------------------------------------------------
+constexpr int GCK = GC + 1, GCN = GC * GC * GCK;                               // 5 x 5 x 6 corners per (tile, camera)
+constexpr int GS_SLOTS = 4, GS_THREADS = 32 * (4 + GS_SLOTS);                  // box slots = producer warps; 4 gather warps
+constexpr int GS_HDR = 1280, GS_META = GCN * 8;                                // header: corners (1200 B), then the int4 box
+constexpr int GS_CORNERS_PER_LANE = (GCN + 31) / 32;
+
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// this lane's corners of tile (ti, tj, tk): offsets in the coarse grid, indices clamped like ATen's reads
+__device__ __forceinline__ void tile_corner_offsets(int lane, int ti, int tj, int tk, int h, int (&go)[GS_CORNERS_PER_LANE])
+{
+#pragma unroll
+    for (int r = 0; r < GS_CORNERS_PER_LANE; ++r) {
+        const int l = min(lane + 32 * r, GCN - 1);
+        const int lk = l % GCK, lj = (l / GCK) % GC, li = l / (GCK * GC);
+        const int gi = min(max(GCELL * ti - 1 + li, 0), h - 1), gj = min(max(GCELL * tj - 1 + lj, 0), h - 1),
+                  gk = min(max(GCELL * tk - 1 + lk, 0), h - 1);
+        go[r] = (gi * h + gj) * h + gk;
+    }
+}
+
+template <int LAYOUT, int MODE>
+__global__ void __launch_bounds__(GS_THREADS, 3)
+gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ cab,
+                     int ncam, int K, int hs, int G, float post_scale, int cap_bytes, void *__restrict__ out_, int total_tiles)
+{
+    extern __shared__ __align__(128) uint8_t gsm[];                            // [GS_SLOTS][cap_bytes] pixel boxes
+    uint8_t *hdrs = gsm + (size_t)GS_SLOTS * cap_bytes;                        // [2 * GS_SLOTS][GS_HDR]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(hdrs + 2 * GS_SLOTS * GS_HDR);
+    uint64_t *full = bars, *empty = bars + GS_SLOTS;
+    const int h = G / 2, nt = G / GT + 1, ntk = G / GT, tiles_fs = nt * nt * ntk;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t nc = (size_t)h * h * h;
+    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GS_SLOTS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= 4) {
+        // =================================== producers ========================================
+        // Producer p owns box slot p and the items n = p, p + GS_SLOTS, ...  (item n = tile n / ncam, camera n % ncam of
+        // this CTA's tile sequence): its chain  corners -> box -> rows  is ~2 us of dependent latency per item, which
+        // one warp cannot sustain per item but GS_SLOTS warps, each with GS_SLOTS gather steps of time per item, can.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int p = warp - 4;
+        const int total = my_tiles * ncam;
+        int go[GS_CORNERS_PER_LANE];
+        int go_tl = -1;
+        const float2 *csrc = cab;
+        auto prefetch = [&](int n) {                                           // corners of item n -> its header (LDGSTS)
+            const int tl = n / ncam, c = n - tl * ncam;
+            if (tl != go_tl) {
+                go_tl = tl;
+                const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+                const int b = t / tiles_fs, r0 = t - b * tiles_fs;
+                const int tk = r0 % ntk, tj = (r0 / ntk) % nt, ti = r0 / (ntk * nt);
+                tile_corner_offsets(lane, ti, tj, tk, h, go);
+                csrc = cab + (size_t)b * ncam * nc;
+            }
+            const float2 *src = csrc + (size_t)c * nc;
+            const uint32_t dst = smem_u32(hdrs + (n % (2 * GS_SLOTS)) * GS_HDR);
+#pragma unroll
+            for (int r = 0; r < GS_CORNERS_PER_LANE; ++r)
+                if (lane + 32 * r < GCN) cp_async8(dst + (uint32_t)(lane + 32 * r) * 8u, src + go[r]);
+            cp_async_commit();
+        };
+        if (p < total) prefetch(p);
+        uint32_t ph = 0;
+        for (int n = p; n < total; n += GS_SLOTS) {
+            cp_async_wait<0>();
+            // pixel box bounding every index of the tile: each ATen lerp is a rounded convex combination, so the fine
+            // coordinates stay inside the corners' range; (v / 2).int() is monotone, so the box is the integer
+            // min / max of the corners' own pixels (REDUX instead of a float shuffle tree)
+            uint8_t *hd = hdrs + (n % (2 * GS_SLOTS)) * GS_HDR;
+            int x0, x1, y0, y1;
+            {
+                const float2 *cn = reinterpret_cast<const float2 *>(hd);
+                const float2 v0 = cn[lane];                                    // this lane's own copies (lane < GCN)
+                x0 = x1 = __float2int_rz(__fmul_rn(v0.x, 0.5f)); y0 = y1 = __float2int_rz(__fmul_rn(v0.y, 0.5f));
+#pragma unroll
+                for (int r = 1; r < GS_CORNERS_PER_LANE; ++r) {
+                    const int l = lane + 32 * r;
+                    const float2 v = cn[l < GCN ? l : lane];
+                    const int px = __float2int_rz(__fmul_rn(v.x, 0.5f)), py = __float2int_rz(__fmul_rn(v.y, 0.5f));
+                    x0 = min(x0, px); x1 = max(x1, px); y0 = min(y0, py); y1 = max(y1, py);
+                }
+                x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+                y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
+            }
+            const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+            // smem row pitch in pixels: == 3 or 5 (mod 8) when that fits the slot (see gather_staged_kernel), else odd,
+            // else the bare width; 0 = the box does not fit and the step gathers from global memory
+            int pitch = bw + (int)((0x45010123u >> (4 * (bw & 7))) & 15u);
+            if (pitch * bh * G_PIX_BYTES > cap_bytes) pitch = bw | 1;
+            if (pitch * bh * G_PIX_BYTES > cap_bytes) pitch = bw;
+            if (pitch * bh * G_PIX_BYTES > cap_bytes || x0 < 0 || y0 < 0 || x1 >= hs || y1 >= hs) pitch = 0;
+            if (lane == 0) *reinterpret_cast<int4 *>(hd + GS_META) = make_int4(x0, y0, p * cap_bytes, pitch);
+            const uint32_t fb = smem_u32(full + p);
+            if (n >= GS_SLOTS) { mbar_wait(smem_u32(empty + p), ph); ph ^= 1u; }   // item n - GS_SLOTS is done: slot + older header free
+            __syncwarp();                                                      // every lane's corner copies + the box precede the arrive
+            if (pitch == 0) {
+                if (lane == 0) mbar_arrive(fb);                                // box too large: gathered from global memory
+            } else {
+                const uint32_t row_bytes = (uint32_t)(bw * G_PIX_BYTES);
+                if (lane == 0) mbar_expect_tx(fb, row_bytes * (uint32_t)bh);
+                __syncwarp();
+                const int tl = n / ncam, c = n - tl * ncam;
+                const int b = ((int)blockIdx.x + tl * (int)gridDim.x) / tiles_fs;
+                uint8_t *box = gsm + (size_t)p * cap_bytes;
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(hm) + ((((size_t)b * ncam + c) * hs + y0) * hs + x0) * G_PIX_BYTES;
+                const int rowB = pitch * G_PIX_BYTES;
+                for (int r = lane; r < bh; r += 32)
+                    bulk_load(smem_u32(box + (size_t)r * rowB), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
+            }
+            if (n + GS_SLOTS < total) prefetch(n + GS_SLOTS);                  // into the header item n - GS_SLOTS just released
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+
+    // =================================== gather warps ========================================
+    const int ci = warp, cj = lane >> 3, z = lane & 7, lk0 = (z + 1) >> 1;
+    const int l0 = (ci * GC + cj) * GCK + lk0;
+    const uint64_t whalf = f2_pack(0.5f, 0.5f);
+    const size_t nv = (size_t)G * G * G;
+    int s = 0; uint32_t ph = 0, hsel = 0;                                      // box slot, its phase, header half (0 / GS_SLOTS)
+    for (int tl = 0; tl < my_tiles; ++tl) {
+        const int t = (int)blockIdx.x + tl * (int)gridDim.x;
+        const int b = t / tiles_fs, r0 = t - b * tiles_fs;
+        const int tk = r0 % ntk, tj = (r0 / ntk) % nt, ti = r0 / (ntk * nt);
+        const int I0 = GT * ti - 1 + 2 * ci, J0 = GT * tj - 1 + 2 * cj, Kz = GT * tk + z;
+        // ATen area_pixel_compute_source_index, scale .5: even fine index -> lambda1 .75, odd -> .25, index 0 -> 0
+        const float lk1 = Kz == 0 ? 0.f : ((z & 1) ? 0.25f : 0.75f), lk0w = __fsub_rn(1.f, lk1);
+        const uint64_t wk0 = f2_pack(lk0w, lk0w), wk1 = f2_pack(lk1, lk1);
+        uint64_t wj1[2], wj0[2], wi1[2], wi0[2];
+        bool vi[2], vj[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const float j1 = (J0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f), j0 = __fsub_rn(1.f, j1);
+            const float i1 = (I0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f), i0 = __fsub_rn(1.f, i1);
+            wj1[v] = f2_pack(j1, j1); wj0[v] = f2_pack(j0, j0); wi1[v] = f2_pack(i1, i1); wi0[v] = f2_pack(i0, i0);
+            vi[v] = (I0 + v) >= 0 && (I0 + v) < G; vj[v] = (J0 + v) >= 0 && (J0 + v) < G;
+        }
+        const bool any = (vi[0] || vi[1]) && (vj[0] || vj[1]);
+        __half2 acc[4][KP / 2];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int i = 0; i < KP / 2; ++i) acc[v][i] = __float2half2_rn(0.f);
+
+        for (int c = 0; c < ncam; ++c) {
+            mbar_wait(smem_u32(full + s), ph);
+            if (any) {
+                const uint8_t *hd = hdrs + (s + (int)hsel) * GS_HDR;
+                const uint64_t *Cn = reinterpret_cast<const uint64_t *>(hd) + l0;                   // (x, y) corner pairs
+                const int4 bx = *reinterpret_cast<const int4 *>(hd + GS_META);
+                const int fits = bx.w, rowB = (fits ? bx.w : hs) * G_PIX_BYTES;
+                const int baseB = fits ? -(bx.y * bx.w + bx.x) * G_PIX_BYTES : 0;
+                uint64_t xk[2][2];
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int l = (p * GC + q) * GCK;
+                        xk[p][q] = lerp2<MODE>(wk0, Cn[l], wk1, Cn[l + 1]);
+                    }
+                int off[4];
+#pragma unroll
+                for (int jv = 0; jv < 2; ++jv) {
+                    uint64_t yj[2];
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) yj[p] = lerp2<MODE>(wj0[jv], xk[p][0], wj1[jv], xk[p][1]);
+#pragma unroll
+                    for (int iv = 0; iv < 2; ++iv) {
+                        float fa, fb2;
+                        f2_unpack(f2_mul(lerp2<MODE>(wi0[iv], yj[0], wi1[iv], yj[1]), whalf), fa, fb2);
+                        const int px = __float2int_rz(fa), py = __float2int_rz(fb2);                // (val/2).int()   repro_layer.py:82-83
+                        off[iv * 2 + jv] = py * rowB + (px * G_PIX_BYTES + baseB);
+                    }
+                }
+                uint4 w[4][3];
+                if (fits) {
+                    const uint8_t *box = gsm + bx.z;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        if (vi[v >> 1] && vj[v & 1]) {
+                            const uint4 *pp = reinterpret_cast<const uint4 *>(box + off[v]);
+                            w[v][0] = pp[0]; w[v][1] = pp[1]; w[v][2] = pp[2];
+                        } else {
+                            w[v][0] = w[v][1] = w[v][2] = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                } else {
+                    const uint8_t *gbase = reinterpret_cast<const uint8_t *>(hm) + ((size_t)b * ncam + c) * hs * hs * G_PIX_BYTES;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        if (vi[v >> 1] && vj[v & 1]) {
+                            const uint4 *pp = reinterpret_cast<const uint4 *>(gbase + off[v]);
+                            w[v][0] = __ldg(pp); w[v][1] = __ldg(pp + 1); w[v][2] = __ldg(pp + 2);
+                        } else {
+                            w[v][0] = w[v][1] = w[v][2] = make_uint4(0, 0, 0, 0);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        const uint32_t ww[4] = {w[v][g].x, w[v][g].y, w[v][g].z, w[v][g].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[v][4 * g + i] = __hadd2(acc[v][4 * g + i], *reinterpret_cast<const __half2 *>(&ww[i]));
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(empty + s));
+            if (++s == GS_SLOTS) { s = 0; ph ^= 1u; hsel ^= GS_SLOTS; }
+        }
+
+        // ---- mean over cameras (+ /255) as one fp32 scale, store ---------------------------------------
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int I = I0 + (v >> 1), J = J0 + (v & 1);
+            if (!(vi[v >> 1] && vj[v & 1])) continue;
+            float m[KP];
+#pragma unroll
+            for (int i = 0; i < KP / 2; ++i) {
+                const float2 f = __half22float2(acc[v][i]);
+                m[2 * i] = f.x * post_scale; m[2 * i + 1] = f.y * post_scale;
+            }
+            if (LAYOUT == JHN_VOL_NCDHW_F32) {
+                float *out = (float *)out_ + (size_t)b * K * nv + ((size_t)I * G + J) * G + Kz;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < K) out[(size_t)k * nv] = m[k];
+            } else {
+                const int CJ = (K + 15) / 16 * 2, Wh = G / 2 + 2;
+                const int sv = ((I & 1) * 2 + (J & 1)) * 2 + (Kz & 1);
+                uint4 *out = (uint4 *)out_;
+                const size_t pos = ((size_t)(I >> 1) + 1) * Wh * Wh + (size_t)((J >> 1) + 1) * Wh + (Kz >> 1) + 1;
+                const size_t chunk_stride = (size_t)Wh * Wh * Wh;
+                const size_t ob = (((size_t)b * 8 + sv) * CJ) * chunk_stride + pos;
+#pragma unroll
+                for (int j = 0; j < KP / 8; ++j) {
+                    if (j < CJ) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(m[8 * j + 2 * i], m[8 * j + 2 * i + 1]);
+                            pk[i] = *reinterpret_cast<uint32_t *>(&h2);
+                        }
+                        out[ob + (size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                for (int jz = KP / 8; jz < CJ; ++jz) out[ob + (size_t)jz * chunk_stride] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+}
+
 template <int LAYOUT>
 static int launch_staged(const ReprojectArgs &a, const __half *hm_cl, const float2 *cab, int cap, cudaStream_t st)
 {
@@ -650,7 +935,39 @@ static int launch_staged(const ReprojectArgs &a, const __half *hm_cl, const floa
 #undef JHN_STAGED
 }
 
-static int pick_gather_cap(int) { return 12288; }                             // bytes of pixel box per ring stage
+template <int LAYOUT>
+static int launch_stream(const ReprojectArgs &a, const __half *hm_cl, const float2 *cab, int cap, cudaStream_t st)
+{
+    const size_t gsmem = (size_t)GS_SLOTS * cap + 2 * GS_SLOTS * GS_HDR + 2 * GS_SLOTS * 8;
+    const int nt = a.G / GT + 1, ntk = a.G / GT;
+    const long long total = (long long)a.B * nt * nt * ntk;
+    if (total * a.ncam > 0x7fffffffLL) return fail(JHN_ERR_SHAPE, "too many gather tiles (%lld)", total);
+    static int ctas = 0;                                                        // 3 resident CTAs per SM
+    if (!ctas) {
+        int dev = 0, sms = 0;
+        JHN_CUDA(cudaGetDevice(&dev));
+        JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        ctas = 3 * sms;
+    }
+    const int grid = (int)(total < ctas ? total : ctas);
+    const float post_scale = HALF_STAGE_UNSCALE / ((float)a.ncam * a.post_divide);
+#define JHN_STREAM(MODE)                                                                                         \
+    {                                                                                                            \
+        auto kern = gather_stream_kernel<LAYOUT, MODE>;                                                          \
+        JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));           \
+        JHN_LAUNCH("gather_stream_kernel", st,                                                                   \
+                   kern<<<grid, GS_THREADS, gsmem, st>>>(hm_cl, cab, a.ncam, a.K, a.hs, a.G, post_scale, cap, \
+                                                         a.volume_out, (int)total));                              \
+        return JHN_OK;                                                                                           \
+    }
+    if (a.lerp_mode == JHN_LERP_FMA_FIRST) JHN_STREAM(JHN_LERP_FMA_FIRST)
+    if (a.lerp_mode == JHN_LERP_FMA_SECOND) JHN_STREAM(JHN_LERP_FMA_SECOND)
+    JHN_STREAM(JHN_LERP_NO_FMA)
+#undef JHN_STREAM
+}
+
+static int pick_gather_cap(int) { return 12288; }                             // bytes of pixel box per ring stage (staged kernel)
+constexpr int GS_CAP = 15360;                                                  // ... per box slot of the streaming kernel
 
 size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
 {
@@ -709,10 +1026,14 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
         // throughput path: fp16 staging copy + staged gather (the index dump needs the in-order kernel below)
         JHN_TRY(launch_relayout<__half>(a, (__half *)hm_cl, st));
         const int cap = pick_gather_cap(a.hs);
-        if (a.layout == JHN_VOL_NCDHW_F32) return launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, cap, st);
+        static const int use_staged = getenv("JHN_GATHER_STAGED") != nullptr;         // A/B switch: the one-tile-per-CTA kernel
+        if (a.layout == JHN_VOL_NCDHW_F32)
+            return use_staged ? launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, cap, st)
+                              : launch_stream<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, GS_CAP, st);
         const int CJ = (a.K + 15) / 16 * 2;
         if (!a.borders_valid) JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
-        return launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, cap, st);
+        return use_staged ? launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, cap, st)
+                          : launch_stream<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, GS_CAP, st);
     }
     JHN_TRY(launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)hm_cl, st));
     return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, cab, st);

@@ -1,8 +1,8 @@
 #!/bin/bash
 # usage (on the GPU box): tools/gpu_quick.sh TAG  -> gather/parity tests + default bench into gpurun_out/TAG_*
 TAG=${1:-quick}
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/${TAG}_pytest.log
-python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+timeout -s KILL ${QUICK_TEST_TIMEOUT:-240} python -m pytest tests -m gpu -x -q --timeout 60 2>&1 | tail -8 > gpurun_out/${TAG}_pytest.log
+timeout -s KILL ${QUICK_BENCH_TIMEOUT:-180} python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 python - <<P
 import json
 d=json.load(open('gpurun_out/${TAG}_bench.json'))
