@@ -751,7 +751,7 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
             if (pitch * bh * G_PIX_BYTES > cap_bytes || x0 < 0 || y0 < 0 || x1 >= hs || y1 >= hs) pitch = 0;
             if (lane == 0) *reinterpret_cast<int4 *>(hd + GS_META) = make_int4(x0, y0, p * cap_bytes, pitch);
             const uint32_t fb = smem_u32(full + p);
-            if (n >= GS_SLOTS) { mbar_wait(smem_u32(empty + p), ph); ph ^= 1u; }   // item n - GS_SLOTS is done: slot + older header free
+            if (n >= GS_SLOTS) { mbar_wait_parked(smem_u32(empty + p), ph); ph ^= 1u; }   // item n - GS_SLOTS is done: slot + older header free
             __syncwarp();                                                      // every lane's corner copies + the box precede the arrive
             if (pitch == 0) {
                 if (lane == 0) mbar_arrive(fb);                                // box too large: gathered from global memory
@@ -906,7 +906,7 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
                         out[ob + (size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
-                for (int jz = KP / 8; jz < CJ; ++jz) out[ob + (size_t)jz * chunk_stride] = make_uint4(0, 0, 0, 0);
+                // chunks KP / 8 .. CJ - 1 (channel padding of the first convolution) stay zero: launch_stream clears them
             }
         }
     }
@@ -1031,7 +1031,14 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
             return use_staged ? launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, cap, st)
                               : launch_stream<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, GS_CAP, st);
         const int CJ = (a.K + 15) / 16 * 2;
-        if (!a.borders_valid) JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
+        if (!a.borders_valid) {
+            JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
+            if (!use_staged && CJ > KP / 8) {                                  // all-padding channel chunks: zeroed here, never written by the kernel
+                const size_t Wh = a.G / 2 + 2, chunk_bytes = Wh * Wh * Wh * 16;
+                JHN_CUDA(cudaMemset2DAsync((char *)a.volume_out + (KP / 8) * chunk_bytes, CJ * chunk_bytes, 0,
+                                           (CJ - KP / 8) * chunk_bytes, (size_t)a.B * 8, st));
+            }
+        }
         return use_staged ? launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, cap, st)
                           : launch_stream<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, GS_CAP, st);
     }

@@ -35,6 +35,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
         "@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity) : "memory");
 }
+// long waits (a producer waiting for its slot): the suspend-time hint parks the warp in hardware until the phase
+// completes instead of spinning through the issue slots the gather warps need
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n.reg .pred P1;\nLAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
