@@ -302,7 +302,7 @@ def main():
     kern = {k: dict(launches=n, ms_per_step=msk / K_steps) for k, (n, msk) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     s_in, s_vol = 4, (4 if precision == "fp32" else 2)
     REPRO = ("coarse_project_kernel", "fine_index_kernel", "relayout_kernel", "gather_mean_kernel", "gather_fused_kernel",
-             "gather_staged_kernel")
+             "gather_staged_kernel", "gather_stream_kernel")
     rp_ms = sum(v["ms_per_step"] for k, v in kern.items() if k in REPRO)
     conv_ms = sum(v["ms_per_step"] for k, v in kern.items() if "conv" in k)
     tail_ms = sum(v["ms_per_step"] for k, v in kern.items() if "centroid" in k)
@@ -318,7 +318,7 @@ def main():
     flop_fam = {"tc_conv3_stacked": fl["res_k3_2C"], "tc_conv_k3_resident": fl["res_k3_2C"], "tc_conv_k3_streamed": fl["res_k3_4C"],
                 "tc_conv_front_k3s2": fl["front_k3s2"], "tc_conv_pool_k2s2": fl["pool_k2s2"], "tc_conv_up_convT": fl["up_convT"],
                 "tc_conv_head_1x1": fl["head_1x1"], "conv3d_f32_kernel<3>": fl["front_k3s2"] + fl["res_k3_2C"] + fl["res_k3_4C"]}
-    byte_fam = {"gather_staged_kernel": B * repro_bytes(sh, 2, s_vol), "gather_fused_kernel": B * repro_bytes(sh, s_vol, s_vol),
+    byte_fam = {"gather_staged_kernel": B * repro_bytes(sh, 2, s_vol), "gather_stream_kernel": B * repro_bytes(sh, 2, s_vol), "gather_fused_kernel": B * repro_bytes(sh, s_vol, s_vol),
                 "gather_mean_kernel": B * repro_bytes(sh, s_vol, s_vol),
                 "relayout_kernel": B * sh.ncam * K * sh.hm ** 2 * (s_in + s_vol),
                 "coarse_project_kernel": B * sh.ncam * h ** 3 * 8,

@@ -64,10 +64,14 @@ int jhn_check_device(int device);
 /* Measurement aids (not part of the drop-in surface; used by bench.py):
  *   jhn_launch_count     kernels launched by this library since load (bench.py "gpu_launches");
  *   jhn_profile_enable   while on, every launch is bracketed by CUDA events on its stream;
- *   jhn_profile_collect  device-sync, then "<kernel>\t<launches>\t<total_ms>\n" per kernel name into buf. */
+ *   jhn_profile_collect  device-sync, then "<kernel>\t<launches>\t<total_ms>\n" per kernel name into buf;
+ *   jhn_debug_set_gather_box_bytes  test hook: capacity of one shared-memory pixel-box slot of the streaming gather
+ *                        (0 = default).  Boxes larger than it take the kernel's global-memory path, so a small
+ *                        value lets tests drive that path on ordinary inputs.  Returns the value in effect. */
 unsigned long long jhn_launch_count(void);
 void jhn_profile_enable(int on);
 int jhn_profile_collect(char *buf, int cap);
+int jhn_debug_set_gather_box_bytes(int bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 — replaces F.pad (jarvis/hybridnet/model.py:65-66) + ReprojectionLayer.forward

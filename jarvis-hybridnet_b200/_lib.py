@@ -36,6 +36,7 @@ SYMBOLS = {
     "jhn_launch_count": (c_ulonglong, []),
     "jhn_profile_enable": (None, [c_int]),
     "jhn_profile_collect": (c_int, [c_char_p, c_int]),
+    "jhn_debug_set_gather_box_bytes": (c_int, [c_int]),
 }
 
 _lib = None
@@ -73,6 +74,11 @@ def check(rc):
 
 def launch_count():
     return int(load().jhn_launch_count())
+
+
+def debug_set_gather_box_bytes(n):
+    """Test hook: pixel-box slot capacity of the streaming gather (0 = default); returns the value in effect."""
+    return int(load().jhn_debug_set_gather_box_bytes(int(n)))
 
 
 def profile(on):

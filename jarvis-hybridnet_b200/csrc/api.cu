@@ -86,6 +86,7 @@ int jhn_abi_version(void) { return 2; }
 unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+int jhn_debug_set_gather_box_bytes(int bytes) { return gather_set_box_bytes(bytes); }
 
 // Synchronises the device, then writes one line per kernel name: "<name>\t<launches>\t<total_ms>\n".
 // Returns the number of bytes written (truncated to `cap`), and clears the records.

@@ -77,6 +77,7 @@ struct ReprojectArgs {
 };
 size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision);
 int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStream_t st);
+int gather_set_box_bytes(int bytes);   // test hook (jhn_debug_set_gather_box_bytes)
 
 // zero the never-written border of a blocked+padded (BP/PS) bf16 tensor of `chunks_total` chunk volumes (conv_tc.cu)
 int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st);

@@ -674,7 +674,7 @@ __device__ __forceinline__ void tile_corner_offsets(int lane, int ti, int tj, in
 template <int LAYOUT, int MODE>
 __global__ void __launch_bounds__(GS_THREADS, 3)
 gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ cab,
-                     int ncam, int K, int hs, int G, float post_scale, int cap_bytes, void *__restrict__ out_, int total_tiles)
+                     int ncam, int K, int hs, int G, float post_scale, int cap_bytes, int box_limit, void *__restrict__ out_, int total_tiles)
 {
     extern __shared__ __align__(128) uint8_t gsm[];                            // [GS_SLOTS][cap_bytes] pixel boxes
     uint8_t *hdrs = gsm + (size_t)GS_SLOTS * cap_bytes;                        // [2 * GS_SLOTS][GS_HDR]
@@ -723,6 +723,7 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
         uint32_t ph = 0;
         for (int n = p; n < total; n += GS_SLOTS) {
             cp_async_wait<0>();
+            __syncwarp();                                                      // all lanes' copies visible to all lanes
             // pixel box bounding every index of the tile: each ATen lerp is a rounded convex combination, so the fine
             // coordinates stay inside the corners' range; (v / 2).int() is monotone, so the box is the integer
             // min / max of the corners' own pixels (REDUX instead of a float shuffle tree)
@@ -743,12 +744,33 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
                 y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
             }
             const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-            // smem row pitch in pixels: == 3 or 5 (mod 8) when that fits the slot (see gather_staged_kernel), else odd,
-            // else the bare width; 0 = the box does not fit and the step gathers from global memory
-            int pitch = bw + (int)((0x45010123u >> (4 * (bw & 7))) & 15u);
-            if (pitch * bh * G_PIX_BYTES > cap_bytes) pitch = bw | 1;
-            if (pitch * bh * G_PIX_BYTES > cap_bytes) pitch = bw;
-            if (pitch * bh * G_PIX_BYTES > cap_bytes || x0 < 0 || y0 < 0 || x1 >= hs || y1 >= hs) pitch = 0;
+            // smem row pitch in pixels.  A pixel vector is three 16-byte bank groups, so two pixels of one LDS.128 phase
+            // (8 lanes = 8 voxels along z) collide iff their linear offsets x + pitch * y agree mod 8.  Which pitch
+            // residue keeps a z run of pixels apart depends on the camera's view of the z axis, so the warp tries the
+            // four odd residues on the tile's central z line (lane = residue x voxel) and takes the one with the fewest
+            // colliding lanes; then the smallest pitch >= bw of that residue that fits the slot, else odd, else the
+            // bare width; 0 = the box does not fit and the step gathers from global memory.
+            int pitch;
+            {
+                const float2 *cn = reinterpret_cast<const float2 *>(hd) + ((GC / 2) * GC + GC / 2) * GCK;
+                const int zz = lane & 7, k0 = (zz + 1) >> 1, res = 2 * (lane >> 3) + 1;
+                const float w1 = (zz & 1) ? 0.25f : 0.75f;
+                const float2 ca = cn[k0], cb = cn[k0 + 1];
+                const int X = __float2int_rz(0.5f * (ca.x + w1 * (cb.x - ca.x))), Y = __float2int_rz(0.5f * (ca.y + w1 * (cb.y - ca.y)));
+                const unsigned grp = 0xffu << (lane & 24);
+                const unsigned same_bank = __match_any_sync(0xffffffffu, ((X + res * Y) & 7) | (res << 3));
+                const unsigned same_pix = __match_any_sync(0xffffffffu, (X & 0xfff) | ((Y & 0xfff) << 12) | (res << 24));
+                const unsigned clash = __ballot_sync(0xffffffffu, (same_bank & ~same_pix & grp) != 0u);
+                const int c1 = __popc(clash & 0xffu), c3 = __popc(clash & 0xff00u), c5 = __popc(clash & 0xff0000u), c7 = __popc(clash >> 24);
+                int best = 3, cost = c3;
+                if (c5 < cost) { best = 5; cost = c5; }
+                if (c1 < cost) { best = 1; cost = c1; }
+                if (c7 < cost) { best = 7; cost = c7; }
+                pitch = bw + ((best - bw) & 7);
+            }
+            if (pitch * bh * G_PIX_BYTES > box_limit) pitch = bw | 1;
+            if (pitch * bh * G_PIX_BYTES > box_limit) pitch = bw;
+            if (pitch * bh * G_PIX_BYTES > box_limit || x0 < 0 || y0 < 0 || x1 >= hs || y1 >= hs) pitch = 0;
             if (lane == 0) *reinterpret_cast<int4 *>(hd + GS_META) = make_int4(x0, y0, p * cap_bytes, pitch);
             const uint32_t fb = smem_u32(full + p);
             if (n >= GS_SLOTS) { mbar_wait_parked(smem_u32(empty + p), ph); ph ^= 1u; }   // item n - GS_SLOTS is done: slot + older header free
@@ -935,6 +957,14 @@ static int launch_staged(const ReprojectArgs &a, const __half *hm_cl, const floa
 #undef JHN_STAGED
 }
 
+constexpr int GS_CAP = 15360;                                                  // bytes per pixel-box slot of the streaming kernel
+static int g_box_limit = GS_CAP;                                               // boxes above this gather from global memory (test hook)
+int gather_set_box_bytes(int bytes)
+{
+    g_box_limit = (bytes <= 0 || bytes > GS_CAP) ? GS_CAP : bytes;
+    return g_box_limit;
+}
+
 template <int LAYOUT>
 static int launch_stream(const ReprojectArgs &a, const __half *hm_cl, const float2 *cab, int cap, cudaStream_t st)
 {
@@ -957,7 +987,7 @@ static int launch_stream(const ReprojectArgs &a, const __half *hm_cl, const floa
         JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));           \
         JHN_LAUNCH("gather_stream_kernel", st,                                                                   \
                    kern<<<grid, GS_THREADS, gsmem, st>>>(hm_cl, cab, a.ncam, a.K, a.hs, a.G, post_scale, cap, \
-                                                         a.volume_out, (int)total));                              \
+                                                         g_box_limit, a.volume_out, (int)total));                              \
         return JHN_OK;                                                                                           \
     }
     if (a.lerp_mode == JHN_LERP_FMA_FIRST) JHN_STREAM(JHN_LERP_FMA_FIRST)
@@ -967,7 +997,6 @@ static int launch_stream(const ReprojectArgs &a, const __half *hm_cl, const floa
 }
 
 static int pick_gather_cap(int) { return 12288; }                             // bytes of pixel box per ring stage (staged kernel)
-constexpr int GS_CAP = 15360;                                                  // ... per box slot of the streaming kernel
 
 size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
 {

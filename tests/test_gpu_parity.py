@@ -103,6 +103,57 @@ def test_volume_bf16_staged_gather(oracle, name):
     assert np.sqrt((err ** 2).mean()) <= 2e-3 * np.abs(want / 255.0).max()
 
 
+@pytest.mark.parametrize("name", ["micro_idx", "stress_idx"])
+def test_streaming_gather_large_shapes(oracle, name):
+    """BASELINE configs 2 and 5 (12 x 256^2 maps on a 64^3 grid; 16 cameras on a 96^3 grid) through the streaming
+    gather, against the oracle's fp32 gather + camera mean."""
+    from jarvis_hybridnet_b200 import ReprojectionLayer
+    sh, x, g = load_case(name)
+    L = ReprojectionLayer(cfg_of(sh), precision="bf16")
+    vol, _ = L.forward_batched(*repro_inputs(x), post_divide=255.0, want_index=False)
+    want, _ = oracle.repro_layer_forward(oracle.pad_heatmaps(x["hm"]), x["c3"], x["chm"], x["cam"], x["intr"],
+                                         x["dist"], sh.G, sh.spacing)
+    got = vol[0].cpu().numpy()
+    np.testing.assert_allclose(got, want / 255.0, rtol=2e-2, atol=2e-2 * 4 / 255)
+    err = np.abs(got - want / 255.0)
+    assert np.sqrt((err ** 2).mean()) <= 2e-3 * np.abs(want / 255.0).max()
+
+
+@pytest.mark.parametrize("name", ["tiny_clamp", "small_mh", "example_mh"])
+def test_streaming_gather_global_path_is_identical(name):
+    """Pixel boxes that do not fit a shared-memory slot are gathered from global memory with the same arithmetic:
+    shrinking the slot (test hook) must not change a single bit of the volume."""
+    from jarvis_hybridnet_b200 import ReprojectionLayer, _lib
+    sh, x, g = load_case(name)
+    L = ReprojectionLayer(cfg_of(sh), precision="bf16")
+    ref, _ = L.forward_batched(*repro_inputs(x), post_divide=255.0, want_index=False)
+    try:
+        for limit in (48, 1536, 4096):            # nothing fits / a few boxes fit / most boxes fit
+            assert _lib.debug_set_gather_box_bytes(limit) == limit
+            got, _ = L.forward_batched(*repro_inputs(x), post_divide=255.0, want_index=False)
+            assert torch.equal(got, ref), limit
+    finally:
+        _lib.debug_set_gather_box_bytes(0)
+
+
+def test_streaming_gather_batched_equals_single():
+    """Persistent CTAs walk tiles of all frame sets in one sequence; the result per frame set must not depend on it
+    (B = 5 is not a multiple of anything in the tile schedule)."""
+    from jarvis_hybridnet_b200 import ReprojectionLayer
+    import jarvis_hybridnet_b200.synth as S
+    sh = S.SMALL
+    cam, intr, dist = S.make_rig(sh.ncam, 11)
+    sets = [S.make_frameset(sh, cam, intr, dist, s) for s in range(5)]
+    L = ReprojectionLayer(cfg_of(sh), precision="bf16")
+    stack = lambda i, dt=None: torch.stack([dev(s[i], dt) for s in sets])
+    rep = lambda a: dev(a)[None].expand(5, *a.shape).contiguous()
+    args = (stack(0), stack(1), stack(2), rep(cam), rep(intr), rep(dist))
+    vol, _ = L.forward_batched(*args, post_divide=255.0, want_index=False)
+    for b in range(5):
+        one, _ = L.forward_batched(*[a[b:b + 1] for a in args], post_divide=255.0, want_index=False)
+        assert torch.equal(one[0], vol[b]), b
+
+
 def test_batched_equals_single(oracle):
     """B frame sets in one launch == B reference-style B=1 forwards."""
     from jarvis_hybridnet_b200 import ReprojectionLayer
