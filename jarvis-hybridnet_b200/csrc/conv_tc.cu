@@ -52,6 +52,8 @@ struct TcProgram {
     int nstages, KC, NOUT, PB, resident, ntaps_total, epi, tile_taps;
     int stage_bytes_a, stage_bytes, nslots;           // smem ring geometry (host computed)
     int w_bytes;                                      // resident weight bytes (0 if streamed)
+    int KC_load;                                      // input chunks that carry real channels: the all-padding chunks
+                                                      // above it are zeroed once in shared memory and never fetched
     TcStage st[MAX_STAGES];
 };
 
@@ -124,6 +126,15 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 128; i += TC_THREADS) bias_s[i] = i < P.NOUT ? L.bias[i] : 0.f;
+    if (P.KC_load < P.KC) {
+        // channel-padding chunks of the A operand: zero in every ring slot, for the whole kernel (TMA never writes them)
+        const int per_slot = (P.KC - P.KC_load) * P.PB;
+        for (int i = threadIdx.x; i < per_slot * P.nslots; i += TC_THREADS) {
+            const int slot = i / per_slot, r = i - slot * per_slot;
+            reinterpret_cast<uint4 *>(ring + (size_t)slot * P.stage_bytes)[(size_t)P.KC_load * P.PB + r] = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -157,13 +168,13 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
                     const int start = p0 + S.pos_off;
                     const int npos = min(P.PB, PP - start);
                     const uint32_t run = (uint32_t)npos * 16;
-                    uint32_t bytes = run * (uint32_t)P.KC;
+                    uint32_t bytes = run * (uint32_t)P.KC_load;
                     if (!P.resident) bytes += (uint32_t)(S.ntaps * tap_bytes);
                     mbar_expect_tx(fb, bytes);
                     const size_t unit0 = ((size_t)(c.b * L.CJ_in + S.chunk0) * Wp + (c.z + S.dz)) * PP + start;
                     const uint8_t *src = reinterpret_cast<const uint8_t *>(L.in) + unit0 * 16;
                     const size_t chunk_stride = (size_t)Wp * PP * 16;
-                    for (int j = 0; j < P.KC; ++j)
+                    for (int j = 0; j < P.KC_load; ++j)
                         bulk_load(smem_u32(dst + (size_t)j * P.PB * 16), src + j * chunk_stride, run, fb);
                     if (!P.resident)
                         bulk_load(smem_u32(dst + P.stage_bytes_a),
@@ -787,6 +798,7 @@ struct TcCtx {
             return c3_launch(T.cout_pad, in, T.w3, T.bias, out, stats, B, D, ns, pb, sms, keep_bias ? 1 : 0, st);
         TcProgram P;
         JHN_TRY(build_program(P, kLayerKind[l], T.cin_pad, T.cout_pad, D, net->tc->max_smem));
+        P.KC_load = (net->desc[l].cin + 7) / 8 < P.KC ? (net->desc[l].cin + 7) / 8 : P.KC;
         TcLaunch L;
         L.in = in; L.w = T.w; L.bias = T.bias; L.out = out; L.stats = stats; L.B = B; L.D = D; L.CJ_in = chunks_in; L.CJ_out = chunks_out;
         L.NT = tiles_per_plane(D); L.total_tiles = B * D * L.NT * P.tile_taps; L.Kout = T.cout;
