@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--ref-sample", type=int, default=2, help="frame sets per reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the B=1 eager / CUDA-graph latency measurement")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -281,6 +282,22 @@ def main():
     e2e = dict(value=world * B * K_steps / e2e_s, unit="frame-sets/s", h2d_bytes_per_step=int(h2d),
                d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * e2e_s / K_steps)
 
+    # ---- B=1 latency (the reference's predictor runs one frame set per call): eager launches vs CUDA-graph replay ----
+    latency = None
+    if rank == 0 and not args.no_latency:
+        one = [t[:1].contiguous() for t in devb[0]]
+        def timed(fn, n=50):
+            for _ in range(5):
+                fn(*one)
+            torch.cuda.synchronize(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter(); a.record()
+            for _ in range(n):
+                fn(*one)
+            b.record(); torch.cuda.synchronize()
+            return dict(device_ms=a.elapsed_time(b) / n, wall_ms=1e3 * (time.perf_counter() - t0) / n)
+        latency = dict(frame_sets=1, eager=timed(net.forward), cuda_graph=timed(net.forward_graph),
+                       note="one frame set per call, inputs resident; graph replay includes the copy into its static inputs")
+
     # ---- the one collective of the job: gather [N,K,4] at the end ---------------------------------
     gather_ms = None
     if world > 1:
@@ -358,7 +375,7 @@ def main():
                                 l2="inputs rotate through %d batches of %.0f MB (>> 126 MB L2)" % (n_pool, B * sh.ncam * sh.K * sh.hm ** 2 * 4 / 1e6),
                                 timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded"),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb,
-                    stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms)
+                    stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms, latency_b1=latency)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

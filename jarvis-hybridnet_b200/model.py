@@ -94,8 +94,9 @@ class HybridNet3D(nn.Module):
             self.v2vNet.load_state_dict(sd, strict=True)
         self._ws = None
         self._host = None
+        self._graphs = {}
 
-    def forward(self, heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients):
+    def forward(self, heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients, _ws=None):
         _lib.require_cuda(heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients)
         lib = _lib.load()
         B, ncam, K, S, _ = heatmaps.shape
@@ -104,8 +105,14 @@ class HybridNet3D(nn.Module):
         net = self.v2vNet._get_handle()
         need = _lib.c_size_t()
         _lib.check(lib.jhn_hybrid3d_workspace_bytes(net, B, ncam, self.hs, self.G, need))
-        if self._ws is None or self._ws.numel() < need.value or self._ws.device != heatmaps.device:
-            self._ws = torch.empty(need.value, dtype=torch.uint8, device=heatmaps.device)
+        if _ws is not None:                                  # a captured graph owns its workspace
+            ws = _ws
+            if ws.numel() < need.value:
+                raise RuntimeError("graph workspace too small")
+        else:
+            if self._ws is None or self._ws.numel() < need.value or self._ws.device != heatmaps.device:
+                self._ws = torch.empty(need.value, dtype=torch.uint8, device=heatmaps.device)
+            ws = self._ws
         dev = heatmaps.device
         pts = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
         conf = torch.empty((B, K), dtype=torch.float32, device=dev)
@@ -117,9 +124,50 @@ class HybridNet3D(nn.Module):
         _lib.check(lib.jhn_hybrid3d_forward(net, _lib.dptr(hm), int(S == self.hs), _lib.dptr(cam), _lib.dptr(intr),
                                             _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm), B, ncam, self.hs, self.G,
                                             float(self.spacing), float(self.roi), self.lerp_mode, _lib.dptr(pts),
-                                            _lib.dptr(conf), _lib.dptr(am), _lib.dptr(self._ws), self._ws.numel(),
+                                            _lib.dptr(conf), _lib.dptr(am), _lib.dptr(ws), ws.numel(),
                                             _lib.stream_ptr()))
         return pts, conf, am
+
+    def workspace_bytes(self, B, ncam):
+        need = _lib.c_size_t()
+        _lib.check(_lib.load().jhn_hybrid3d_workspace_bytes(self.v2vNet._get_handle(), B, ncam, self.hs, self.G, need))
+        return int(need.value)
+
+    def forward_graph(self, heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients):
+        """forward() replayed from a CUDA graph: the low-latency path for small B (the reference's predictor runs one
+        frame set per call, jarvis3D.py:178-186, where the 27 launches of a forward cost more on the host than on
+        the device).  The first call per input signature captures the graph over static input / output buffers and
+        a workspace it owns; later calls copy the inputs in and replay.  The library is capture-safe by contract
+        (stream-ordered, no allocation, no synchronisation: SURVEY.md §8b).  The returned tensors are the graph's
+        static outputs: consume them before the next call with the same signature."""
+        ins = (heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients)
+        _lib.require_cuda(*ins)
+        dts = (torch.float32, torch.int32, torch.int32, torch.float32, torch.float32, torch.float32)
+        key = (tuple(tuple(t.shape) for t in ins), heatmaps.device)
+        ent = self._graphs.get(key)
+        if ent is None:
+            B, ncam = heatmaps.shape[0], heatmaps.shape[1]
+            static = [torch.empty(t.shape, dtype=dt, device=t.device) for t, dt in zip(ins, dts)]
+            ws = torch.empty(self.workspace_bytes(B, ncam), dtype=torch.uint8, device=heatmaps.device)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=heatmaps.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                    # warm-up on the graph's workspace: zero borders, attributes
+                for d, t in zip(static, ins):
+                    d.copy_(t)
+                for _ in range(2):
+                    self.forward(*static, _ws=ws)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.forward(*static, _ws=ws)
+            ent = self._graphs[key] = (graph, static, out, ws)
+        graph, static, out, _ = ent
+        for d, t in zip(static, ins):
+            d.copy_(t)
+        graph.replay()
+        return out
 
     def forward_host(self, host_inputs, chunk=4):
         """End-to-end call with HOST (pinned) tensors: H2D copies of the six inputs, the fused forward, and a

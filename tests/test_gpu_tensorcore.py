@@ -142,3 +142,23 @@ def test_bf16_batch_matches_single(oracle):
         assert (p1[0] - pts[b]).abs().max().item() < 2e-2              # atomics reorder the fp32 statistics sums
         want = oracle.hybrid3d_forward(w, sets[b][0], sets[b][1], sets[b][2], cam, intr, dist, sh.roi, sh.spacing)
         assert np.abs(pts[b].cpu().numpy() - want["points"]).max() < 0.5
+
+
+def test_forward_graph_replay_equals_forward():
+    """CUDA-graph replay (the B=1 latency path) returns what the eager call returns, for changing inputs (the
+    InstanceNorm statistics are summed with atomics, so runs agree to bf16 rounding noise, not bit for bit)."""
+    import jarvis_hybridnet_b200.synth as S
+    from jarvis_hybridnet_b200 import HybridNet3D
+    sh = S.SMALL
+    cam, intr, dist = S.make_rig(sh.ncam, 3)
+    net = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, S.make_v2v_weights(sh.K, 0, "he"), precision="bf16").cuda()
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()[None]
+    for seed in (0, 1, 2):
+        hm, c3, chm, _ = S.make_frameset(sh, cam, intr, dist, seed)
+        args = (d(hm), d(c3), d(chm), d(cam), d(intr), d(dist))
+        want = [t.clone() for t in net(*args)]
+        got = net.forward_graph(*args)
+        torch.cuda.synchronize()
+        assert torch.allclose(got[0], want[0], rtol=0, atol=5e-2), (seed, (got[0] - want[0]).abs().max())
+        assert torch.allclose(got[1], want[1], rtol=0, atol=1e-3)
+    assert len(net._graphs) == 1
