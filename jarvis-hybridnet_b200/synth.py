@@ -159,3 +159,26 @@ def make_v2v_weights(K, seed=0, scale="he"):
         sd[name + ".weight"] = w.astype(np.float32)
         sd[name + ".bias"] = b.astype(np.float32)
     return sd
+
+
+def make_center_case(ncam, cam, intr, dist, seed=0, cdis=256, noise=2.0, n_weak=0, small_images=False):
+    """Inputs of the predictor glue (jarvis/prediction/jarvis3D.py:143-178) for one frame set:
+    centre-detect heat maps [ncam,1,cdis/2,cdis/2] (a Gaussian of amplitude 255, sigma 2 px at the projected
+    centre, plus N(0, noise); the last `n_weak` cameras only reach amplitude 30, i.e. stay under the reference's
+    detection threshold of 50), full images [ncam,3,H,W] fp32 in [0,1] and the true centre [3] (mm).
+    `small_images`: 320 x 256 images instead of 1280 x 1024 (same geometry scaled by 1/4) for cheap fixtures."""
+    rng = np.random.default_rng(5000 + seed)
+    centre = rng.uniform(-100.0, 100.0, 3)
+    W, H = (IMG_W // 4, IMG_H // 4) if small_images else (IMG_W, IMG_H)
+    px = project(centre[None], cam, intr, dist)[:, 0, :]             # full-resolution pixels
+    hc = cdis // 2
+    loc = px / (np.array([W / cdis, H / cdis]) * 2.0)                # jarvis3D.py:157-159 inverted
+    ys = np.arange(hc)[None, :, None]
+    xs = np.arange(hc)[None, None, :]
+    amp = np.full(ncam, 255.0)
+    if n_weak:
+        amp[ncam - n_weak:] = 30.0
+    g = amp[:, None, None] * np.exp(-((xs - loc[:, 0, None, None]) ** 2 + (ys - loc[:, 1, None, None]) ** 2) / (2 * 2.0 ** 2))
+    g = g + rng.normal(0.0, noise, g.shape)
+    imgs = rng.random((ncam, 3, H, W), dtype=np.float32)
+    return g[:, None].astype(np.float32), imgs, centre
