@@ -153,6 +153,37 @@ int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps
                          float *points, float *conf, int32_t *argmax,
                          void *workspace, size_t workspace_bytes, jhn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Predictor glue — replaces, without host synchronisation, the lines of
+ * JarvisPredictor3D.forward between the centre-detect CNN and the 3D network
+ * (jarvis/prediction/jarvis3D.py:147-177) and the two ReprojectionTool methods they call
+ * (jarvis/utils/reprojection.py:45-66 reprojectPoint, :69-90 reconstructPoint).
+ *
+ * jhn_center_locate: per-camera argmax of the centre heat maps, detection count (max > threshold, the
+ *   reference uses 50), weighted DLT triangulation of the centre from all cameras, projection into every
+ *   camera, truncation and clamping of the crop centres.
+ *     center_heatmaps device fp32 [B][ncam][Hc][Wc] (centre-detect output [1]); img_w / img_h full image size;
+ *     center_detect_img_size cfg.CENTERDETECT.IMAGE_SIZE; bbox_hw = BOUNDING_BOX_SIZE / 2; ncam <= 64
+ *     preds     device i32 [B][ncam][2] (x, y) in heat-map pixels      maxvals device fp32 [B][ncam] (max / 255)
+ *     center3D  device fp32 [B][3] (mm)     center3D_int device i32 [B][3] (center3D.int())
+ *     centerHM  device i32 [B][ncam][2] (full-resolution pixels, clamped to [bbox_hw, size - bbox_hw])
+ *     valid     device i32 [B]: 1 iff at least two cameras detected the centre (the reference returns None
+ *               otherwise); when 0 the other outputs of that frame set are zeros / bbox_hw
+ *     scratch   device, 8 * B bytes, zeroed once by the caller (the kernel leaves it zeroed)
+ * jhn_crop_normalize: jarvis3D.py:168-177, imgs device fp32 [B][ncam][3][H][W] -> crops device fp32
+ *   [B][ncam][3][bbox][bbox] = (window around centerHM - mean) / std; zeros for frame sets with valid == 0.
+ *   mean / std: 3 host floats each (cfg.DATASET.MEAN / STD).  bbox must be a multiple of 4.
+ * ------------------------------------------------------------------------------------------------ */
+int jhn_center_locate(const float *center_heatmaps, int B, int ncam, int Hc, int Wc, int img_w, int img_h,
+                      int center_detect_img_size, int bbox_hw, float threshold,
+                      const float *cameraMatrices, const float *intrinsicMatrices,
+                      const float *distortionCoefficients, int32_t *preds, float *maxvals, float *center3D,
+                      int32_t *center3D_int, int32_t *centerHM, int32_t *valid, void *scratch,
+                      jhn_stream_t stream);
+int jhn_crop_normalize(const float *imgs, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
+                       const int32_t *valid, const float *mean, const float *std, float *crops,
+                       jhn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

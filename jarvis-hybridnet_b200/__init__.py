@@ -8,7 +8,8 @@ __version__ = "0.1.0"
 def __getattr__(name):
     import importlib
     table = {"ReprojectionLayer": "repro_layer", "V2VNet": "v2vnet", "HybridNet3D": "model", "accelerate": "model",
-             "centroid_tail": "model", "shard_range": "model", "gather_results": "model"}
+             "centroid_tail": "model", "shard_range": "model", "gather_results": "model",
+             "locate_center": "predictor", "crop_normalize": "predictor", "accelerate_predictor": "predictor"}
     if name in table:
         return getattr(importlib.import_module("." + table[name], __name__), name)
     raise AttributeError(name)

@@ -32,6 +32,9 @@ SYMBOLS = {
     "jhn_hybrid3d_workspace_bytes": (c_int, [_P, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "jhn_hybrid3d_forward": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float,
                                      c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "jhn_center_locate": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P,
+                                  _P, _P, _P, _P, _P, _P, _P, _P]),
+    "jhn_crop_normalize": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, POINTER(c_float), POINTER(c_float), _P, _P]),
     # not part of the drop-in surface: launch counter used by bench.py's `gpu_launches`
     "jhn_launch_count": (c_ulonglong, []),
     "jhn_profile_enable": (None, [c_int]),

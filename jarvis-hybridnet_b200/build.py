@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjarvis_hybridnet_b200%s.so" % os.environ.get("JHN_LIB_SUFFIX", ""))   # suffix: experiment builds
-SOURCES = ["api.cu", "repro.cu", "conv_f32.cu", "conv_tc.cu", "conv3_tc.cu", "head_tc.cu", "tail.cu"]
+SOURCES = ["api.cu", "repro.cu", "conv_f32.cu", "conv_tc.cu", "conv3_tc.cu", "head_tc.cu", "tail.cu", "center.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
 

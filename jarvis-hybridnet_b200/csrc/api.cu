@@ -298,6 +298,35 @@ int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps
     return jhn_centroid_reduce(vout, B, net->K, h, spacing, roi, center3D, points, conf, argmax, stream);
 }
 
+int jhn_center_locate(const float *center_heatmaps, int B, int ncam, int Hc, int Wc, int img_w, int img_h,
+                      int center_detect_img_size, int bbox_hw, float threshold, const float *cameraMatrices,
+                      const float *intrinsicMatrices, const float *distortionCoefficients, int32_t *preds,
+                      float *maxvals, float *center3D, int32_t *center3D_int, int32_t *centerHM, int32_t *valid,
+                      void *scratch, jhn_stream_t stream)
+{
+    if (!center_heatmaps || !cameraMatrices || !intrinsicMatrices || !distortionCoefficients || !preds || !maxvals ||
+        !center3D || !center3D_int || !centerHM || !valid || !scratch)
+        return fail(JHN_ERR_ARG, "jhn_center_locate: null pointer argument");
+    if (B < 1 || B > 65535 || ncam < 1 || ncam > 64) return fail(JHN_ERR_SHAPE, "need 1<=B<=65535, 1<=ncam<=64 (got B=%d ncam=%d)", B, ncam);
+    if (Hc < 1 || Wc < 1 || (long long)Hc * Wc > (1 << 26)) return fail(JHN_ERR_SHAPE, "centre heat map %dx%d out of range", Hc, Wc);
+    if (center_detect_img_size < 1 || bbox_hw < 1 || img_w < 2 * bbox_hw || img_h < 2 * bbox_hw)
+        return fail(JHN_ERR_SHAPE, "image %dx%d smaller than the bounding box (half width %d)", img_w, img_h, bbox_hw);
+    return center_locate_launch(center_heatmaps, B, ncam, Hc, Wc, img_w, img_h, center_detect_img_size, bbox_hw, threshold,
+                                cameraMatrices, intrinsicMatrices, distortionCoefficients, preds, maxvals, center3D,
+                                center3D_int, centerHM, valid, scratch, (cudaStream_t)stream);
+}
+
+int jhn_crop_normalize(const float *imgs, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
+                       const int32_t *valid, const float *mean, const float *std, float *crops, jhn_stream_t stream)
+{
+    if (!imgs || !centerHM || !valid || !mean || !std || !crops) return fail(JHN_ERR_ARG, "jhn_crop_normalize: null pointer argument");
+    if (B < 1 || ncam < 1 || (long long)B * ncam > 65535) return fail(JHN_ERR_SHAPE, "need B*ncam in [1,65535] (got B=%d ncam=%d)", B, ncam);
+    if (bbox < 4 || (bbox % 4) != 0 || bbox > H || bbox > W) return fail(JHN_ERR_SHAPE, "bounding box %d must be a multiple of 4 and fit the %dx%d image", bbox, W, H);
+    for (int i = 0; i < 3; ++i)
+        if (!(std[i] > 0.f)) return fail(JHN_ERR_ARG, "std[%d] must be > 0", i);
+    return crop_normalize_launch(imgs, B, ncam, H, W, bbox, centerHM, valid, mean, std, crops, (cudaStream_t)stream);
+}
+
 }  // extern "C"
 
 namespace jhn {

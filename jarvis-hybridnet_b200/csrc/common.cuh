@@ -85,4 +85,11 @@ int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st
 int centroid_launch(const float *v, int B, int K, int h, float spacing, float roi, const int32_t *center3D,
                     float *points, float *conf, int32_t *argmax, cudaStream_t st);
 
+int center_locate_launch(const float *hm, int B, int ncam, int Hc, int Wc, int img_w, int img_h, int cdis, int bbox_hw,
+                         float threshold, const float *cam, const float *intr, const float *dist, int32_t *preds,
+                         float *maxvals, float *center3D, int32_t *center3D_int, int32_t *centerHM, int32_t *valid,
+                         void *scratch, cudaStream_t st);
+int crop_normalize_launch(const float *imgs, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
+                          const int32_t *valid, const float *mean, const float *std, float *out, cudaStream_t st);
+
 }  // namespace jhn
