@@ -32,6 +32,8 @@ WORKLOADS = {
     "c2_micro": dict(shape=S.MICRO, batch=8),
     "c5_stress": dict(shape=S.STRESS, batch=8),
     "tiny": dict(shape=S.TINY, batch=4),
+    # the predictor glue (centre localisation + crops) in front of the 3D path
+    "f1_predictor_glue": dict(shape=S.EXAMPLE, batch=8),
 }
 
 
@@ -183,6 +185,91 @@ def cpu_baseline(sh, budget_s=12.0):
                        f"(C index/gather/tail on {cores} threads + torch-CPU V2V)")
 
 
+def run_glue(args, wl):
+    """--workload f1_predictor_glue: jhn_center_locate + jhn_crop_normalize (jarvis3D.py:147-177) for `batch` frame sets
+    per step: 12 cameras, 128^2 centre heat maps, 1280x1024 fp32 images, 256^2 crops.  Same JSON contract; the
+    roofline is the crop kernel's (HBM: window read + crop written)."""
+    import torch
+    from jarvis_hybridnet_b200 import _lib, crop_normalize, locate_center
+    from oracle import center_oracle as C
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1 or args.gpus != 1:
+        raise SystemExit("f1_predictor_glue is a single-GPU microbenchmark")
+    torch.cuda.set_device(0)
+    sh, B = wl["shape"], wl["batch"]
+    cdis, bbox, MEAN, STD = 256, sh.bbox, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    cam, intr, dist = S.make_rig(sh.ncam, 0)
+    cases = [S.make_center_case(sh.ncam, cam, intr, dist, s, cdis) for s in range(2)]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    n_pool = 2                                                                   # 2 x B x 189 MB of images >> L2
+    hm_h = [torch.stack([t(cases[(i + p) % 2][0][:, 0]) for i in range(B)]).pin_memory() for p in range(n_pool)]
+    im_h = [torch.stack([t(cases[(i + p) % 2][1]) for i in range(B)]).pin_memory() for p in range(n_pool)]
+    rep = lambda a: t(a)[None].expand(B, *a.shape).contiguous().cuda()
+    camd, intrd, distd = rep(cam), rep(intr), rep(dist)
+    hm_d, im_d = [x.cuda() for x in hm_h], [x.cuda() for x in im_h]
+    scratch = torch.zeros(2 * B, dtype=torch.int32, device="cuda")
+
+    def step(hm, im):
+        loc = locate_center(hm, (S.IMG_W, S.IMG_H), cdis, bbox // 2, camd, intrd, distd, scratch=scratch)
+        return loc, crop_normalize(im, loc["centerHM"], loc["valid"], bbox, MEAN, STD)
+
+    K_steps, W = args.steps, max(args.warmup, 3)
+    clk = ClockSampler(0)
+    for i in range(W):
+        step(hm_d[i % n_pool], im_d[i % n_pool])
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K_steps):
+        loc, crops = step(hm_d[i % n_pool], im_d[i % n_pool])
+    e1.record(); torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    # end to end: host images + heat maps in, crops stay on the device for the 3D network, centres read back
+    hbuf, ibuf = torch.empty_like(hm_d[0]), torch.empty_like(im_d[0])
+    t0 = time.perf_counter()
+    for i in range(K_steps):
+        hbuf.copy_(hm_h[i % n_pool], non_blocking=True); ibuf.copy_(im_h[i % n_pool], non_blocking=True)
+        loc, crops = step(hbuf, ibuf)
+        chm = loc["centerHM"].cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = clk.stop()
+    _lib.profile(True)
+    for i in range(K_steps):
+        step(hm_d[i % n_pool], im_d[i % n_pool])
+    prof = _lib.profile_collect(); _lib.profile(False)
+    kern = {k: dict(launches=n, ms_per_step=msk / K_steps) for k, (n, msk) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    pk = peaks()
+    crop_bytes = B * sh.ncam * 3 * bbox * bbox * 4 * 2
+    cms = prof["crop_normalize_kernel"][1] / prof["crop_normalize_kernel"][0]
+    roof = dict(kernel="crop_normalize_kernel", bound="hbm", achieved=crop_bytes / (cms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
+                frac=crop_bytes / (cms * 1e-3) / 1e9 / pk["hbm"], traffic=None, peak_source=pk["src"],
+                algorithmic_bytes_per_launch=crop_bytes, avg_launch_ms=cms)
+    cb = None
+    if not args.no_cpu_baseline:
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 8.0:
+            r = C.locate_center(cases[n % 2][0], S.IMG_W, S.IMG_H, cdis, bbox // 2, cam, intr, dist)
+            C.crop_normalize(cases[n % 2][1], r["centerHM"], bbox // 2, MEAN, STD)
+            n += 1
+        dt = time.perf_counter() - t0
+        cb = dict(value=n / dt, unit="frame-sets/s", cores=1, kind="port",
+                  sample="%d frame set(s) in %.1f s, numpy oracle port of jarvis3D.py:147-177 (1 thread)" % (n, dt))
+    h2d = hm_h[0].numel() * 4 + im_h[0].numel() * 4
+    line = dict(metric="frame_sets_per_sec", value=B * K_steps / (ms * 1e-3), unit="frame-sets/s", n_gpus=1, steps=K_steps, warmup=W,
+                ms_per_step=ms / K_steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="f1_predictor_glue", ncam=sh.ncam, center_heatmap=cdis // 2, image=[S.IMG_W, S.IMG_H], bbox=bbox,
+                            frame_sets_per_step_per_gpu=B, l2="inputs rotate through 2 batches of %.0f MB (>> 126 MB L2)" % (h2d / 1e6),
+                            timed_region="centre heat maps + images -> crop centres, centre3D, normalised crops (jarvis3D.py:147-177)"),
+                clocks=clocks, e2e=dict(value=B * K_steps / e2e_s, unit="frame-sets/s", h2d_bytes_per_step=int(h2d),
+                                        d2h_bytes_per_step=int(chm.numel() * 4), ms_per_step=1e3 * e2e_s / K_steps),
+                gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, kernels=kern)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -199,6 +286,8 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
         wl["batch"] = args.batch
+    if args.workload == "f1_predictor_glue":
+        return run_glue(args, wl)
     if args.impl == "reference":
         return run_reference(args, wl)
 

@@ -25,10 +25,12 @@ __device__ __forceinline__ void jacobi4(double (&A)[4][4], double (&V)[4][4])
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) V[i][j] = i == j ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 16; ++sweep) {
-        double off = 0.0;
-        for (int p = 0; p < 4; ++p)
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < 4; ++p) {
+            diag += A[p][p] * A[p][p];
             for (int q = p + 1; q < 4; ++q) off += A[p][q] * A[p][q];
-        if (off == 0.0) break;
+        }
+        if (off <= 1e-30 * diag) break;                               // off-diagonal mass below fp64 rounding of the diagonal
         for (int p = 0; p < 4; ++p)
             for (int q = p + 1; q < 4; ++q) {
                 if (A[p][q] == 0.0) continue;
