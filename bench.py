@@ -37,6 +37,27 @@ WORKLOADS = {
 }
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Rank 0 prints ONE JSON line on stdout.  Libraries (NCCL's version banner, torch warnings) write to fd 1 behind
+    Python's back, so fd 1 is pointed at stderr for the whole run and the line goes to a private copy of the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def v2v_flops(sh):
     """Exact un-padded 2*MAC of V2VNet per frame set (SURVEY.md §8a layer table), by kernel family."""
     K, h, q = sh.K, sh.h, sh.h // 2
@@ -160,7 +181,7 @@ def run_reference(args, wl):
                                   sample=f"{sample} frame set(s) of the workload shape per step, {args.steps} steps, "
                                          f"oracle port of the reference (C index/gather/tail + torch-CPU V2V)"),
                 e2e=dict(value=v, unit="frame-sets/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(sh, budget_s=12.0):
@@ -267,7 +288,7 @@ def run_glue(args, wl):
                 clocks=clocks, e2e=dict(value=B * K_steps / e2e_s, unit="frame-sets/s", h2d_bytes_per_step=int(h2d),
                                         d2h_bytes_per_step=int(chm.numel() * 4), ms_per_step=1e3 * e2e_s / K_steps),
                 gpu_launches=int(launches), roofline=roof, cpu_baseline=cb, kernels=kern)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -283,6 +304,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the B=1 eager / CUDA-graph latency measurement")
     args = ap.parse_args()
+    claim_stdout()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
         wl["batch"] = args.batch
@@ -465,7 +487,7 @@ def main():
                                 timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded"),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb,
                     stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms, latency_b1=latency)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

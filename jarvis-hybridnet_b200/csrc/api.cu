@@ -82,7 +82,7 @@ using namespace jhn;
 extern "C" {
 
 const char *jhn_last_error(void) { return g_err; }
-int jhn_abi_version(void) { return 2; }
+int jhn_abi_version(void) { return 3; }
 unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }

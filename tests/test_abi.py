@@ -31,7 +31,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 
 def test_abi_version(lib):
-    assert lib.jhn_abi_version() == 2
+    assert lib.jhn_abi_version() == 3
 
 
 def test_shape_validation_without_gpu(lib):
