@@ -21,7 +21,7 @@
 //                not resident) into a ring of shared-memory slots, completion on mbarriers
 //     warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M=128, N=Cout_pad, K=16,
 //                descriptors formed from a per-tile offset list precomputed in shared memory
-//     warps 2-5  epilogue: tcgen05.ld -> bias -> pad mask -> bf16 store (coalesced 512 B per chunk) and
+//     warps 2-9  epilogue, two per TMEM lane quadrant on alternate 16-column chunks: tcgen05.ld -> bias -> pad mask -> bf16 store and
 //                per-channel sum / sum-of-squares for the following InstanceNorm (fused statistics)
 // Weights of the C->C 3x3x3 layers (124 KB bf16) stay resident in shared memory for the CTA's lifetime.
 // The work of a layer is a "stage program" (TcProgram) built on the host: per tile a list of TMA boxes and,
@@ -74,10 +74,11 @@ struct TcLaunch {
 // ------------------------------------------------------------------------------------------------
 // the implicit-GEMM kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                      // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int TC_EPI_WARPS = 8;
 constexpr int EPI_TILE_FLOATS = 32 * 17;
 constexpr int MAX_DESC = 768;                         // descriptor pairs: (MMAs per tile) x (ring slots)
-constexpr int TC_SMEM_TAIL = 4 * EPI_TILE_FLOATS * 4 + 128 * 4 + 30 * 8 + MAX_DESC * 8 + 1024;
+constexpr int TC_SMEM_TAIL = TC_EPI_WARPS * EPI_TILE_FLOATS * 4 + 128 * 4 + 30 * 8 + MAX_DESC * 8 + 1024;
 
 struct TileCoord { int b, z, pt, tap; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const TcLaunch &L, int tile_taps)
@@ -102,7 +103,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
     uint8_t *w_smem = smem;                                            // resident weights
     uint8_t *ring = smem + P.w_bytes;                                  // nslots x stage_bytes
     float *epi_tiles = reinterpret_cast<float *>(ring + (size_t)P.nslots * P.stage_bytes);
-    float *bias_s = epi_tiles + 4 * EPI_TILE_FLOATS;
+    float *bias_s = epi_tiles + TC_EPI_WARPS * EPI_TILE_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 128);
     uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *wbar = bars + 20;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
@@ -121,7 +122,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
     for (int s = 0; s < P.nstages; ++s) dual = dual && (P.st[s].ntaps * (P.KC / 2) >= 2);
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.nslots; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), TC_EPI_WARPS); }
         mbar_init(smem_u32(wbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -258,7 +259,10 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
         }
     } else {
         // =================================== epilogue warps =================================
+        // two warps per TMEM lane quadrant (warp % 4), taking alternate 16-column chunks: the per-tile chain
+        // tcgen05.ld -> pack -> store -> statistics is latency-bound, so a second warp per scheduler halves it
         const int wq = warp & 3;                                     // TMEM lane quarter this warp may read
+        const int chalf = (warp - 2) >> 2;                           // which chunks: ci % 2 == chalf
         const int m = wq * 32 + lane;                                // GEMM row == position offset in the tile
         float *tile = epi_tiles + (warp - 2) * EPI_TILE_FLOATS;
         const int col = lane & 15, which = lane >> 4;                // statistics ownership
@@ -272,7 +276,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
                 if (stat_b >= 0) {
 #pragma unroll
                     for (int ci = 0; ci < 6; ++ci)
-                        if (ci * 16 < P.NOUT) { atomicAdd(L.stats + ((size_t)stat_b * P.NOUT + ci * 16 + col) * 2 + which, acc_stat[ci]); acc_stat[ci] = 0.f; }
+                        if (ci * 16 < P.NOUT && (ci & 1) == chalf) { atomicAdd(L.stats + ((size_t)stat_b * P.NOUT + ci * 16 + col) * 2 + which, acc_stat[ci]); acc_stat[ci] = 0.f; }
                 }
                 stat_b = c.b;
             }
@@ -284,7 +288,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
 #pragma unroll
             for (int ci = 0; ci < 6; ++ci) {
                 const int c0 = ci * 16;
-                if (c0 < P.NOUT) {
+                if (c0 < P.NOUT && (ci & 1) == chalf) {
                     uint32_t r[16];
                     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ab * 2 * P.NOUT + c0);
                     tc_ld16(taddr, r);
@@ -335,9 +339,10 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
 #pragma unroll
                             for (int i = 0; i < 16; ++i) tile[lane * 17 + i] = v[i];
                             __syncwarp();
-                            float s = 0.f;
-                            for (int rr = 0; rr < 32; ++rr) { const float x = tile[rr * 17 + col]; s += which ? x * x : x; }
-                            acc_stat[ci] += s;
+                            float s4[4] = {0.f, 0.f, 0.f, 0.f};              // four independent chains instead of one of 32
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) { const float x = tile[rr * 17 + col]; s4[rr & 3] += which ? x * x : x; }
+                            acc_stat[ci] += (s4[0] + s4[1]) + (s4[2] + s4[3]);
                             __syncwarp();
                         }
                     }
@@ -351,7 +356,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
         if (L.stats && stat_b >= 0) {
 #pragma unroll
             for (int ci = 0; ci < 6; ++ci)
-                if (ci * 16 < P.NOUT) atomicAdd(L.stats + ((size_t)stat_b * P.NOUT + ci * 16 + col) * 2 + which, acc_stat[ci]);
+                if (ci * 16 < P.NOUT && (ci & 1) == chalf) atomicAdd(L.stats + ((size_t)stat_b * P.NOUT + ci * 16 + col) * 2 + which, acc_stat[ci]);
         }
     }
     tc_fence_before();
