@@ -16,14 +16,14 @@
 //   relayout_kernel        [ncam][K][S][S] planar fp32 -> channels-last [ncam][hs][hs][KP] (fp32 or bf16)
 //                          with the 1-px zero border of F.pad materialised, so that one voxel x camera
 //                          gather is a single contiguous KP-vector instead of K strided scalars.
-//   gather_fused_kernel    per 8x8x8 voxel tile: coarse corner coordinates of all cameras -> smem, phase A
-//                          above, then phase B = index_select + mean over cameras (+ /255): each thread owns
-//                          two voxels, a warp covers a 4x8 patch of one x-slice (compact pixel footprint ->
-//                          few distinct cache lines per request), vector loads of the KP-vector per camera,
-//                          cameras accumulated in order.  Writes NCDHW fp32 or the bf16 parity-split layout
-//                          of the first tensor-core convolution.
+//   gather_fused_kernel    (fp32 parity path, and whenever the int32 index dump is requested) per 8x8x8 voxel
+//                          tile: coarse corner coordinates of all cameras -> smem, phase A above, then phase B =
+//                          index_select + mean over cameras (+ /255), cameras accumulated in order.  Writes NCDHW
+//                          fp32 or the bf16 parity-split layout of the first tensor-core convolution.
+//   gather_stream_kernel   (bf16 throughput path) the same arithmetic as a persistent, warp-specialised kernel:
+//                          pixel boxes of a channels-last fp16 staging copy are TMA-staged in shared memory and
+//                          gathered with LDS.128; see the block comment above the kernel.
 #include <cuda_fp16.h>
-#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -105,7 +105,7 @@ coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ i
     }
 }
 
-// fp16 staging of the staged gather: values are scaled by 2^-4 (exact) so that the sum over up to 64 cameras
+// fp16 staging of the streaming gather: values are scaled by 2^-4 (exact) so that the sum over up to 64 cameras
 // of heat-map values as large as 16 000 stays inside the fp16 range; the gather multiplies the sum back.
 constexpr float HALF_STAGE_SCALE = 0.0625f, HALF_STAGE_UNSCALE = 16.f;
 
@@ -361,33 +361,11 @@ gather_fused_kernel(const T *__restrict__ hm, const float2 *__restrict__ cab, in
 
 
 // ------------------------------------------------------------------------------------------------
-// Staged gather (bf16 throughput path).  One CTA = one 8x8x8 tile of fine voxels, shifted by one voxel
-// (tile t covers fine indices 8t-1 .. 8t+6) so that it is exactly 4x4x4 coarse cells: every cell is the 8
-// fine voxels that interpolate between the same 8 coarse corners, and a tile needs 5^3 corners per camera.
-//
-//   warp 4 (producer)   per camera: the tile's 125 corner coordinates -> shared memory, their min / max ->
-//                       the pixel box that bounds every index of the tile (each ATen lerp is a rounded convex
-//                       combination, so the fine coordinates stay inside the corners' range), then one TMA
-//                       bulk copy (cp.async.bulk, SASS UBLKCP) per box row of the channels-last fp16 staging
-//                       copy into a ring of G_STAGES shared-memory stages, completion on an mbarrier.
-//   warps 0-3 (gather)  thread = (coarse cell, k-parity) = 4 fine voxels sharing the separable lerps:
-//                       indices in registers (bit-identical arithmetic to gather_fused_kernel phase A), then
-//                       per (voxel, camera) three LDS.128 of the pixel's 24-channel fp16 vector and 12 HADD2.
-//                       A quarter-warp is 8 consecutive voxels along z: neighbouring pixels, distinct banks.
-//   The camera sum is accumulated in fp16 (values pre-scaled by 2^-4), converted to fp32 once, then
-//   / ncam, / post_divide as separately rounded fp32 divisions like the fp32 path.  Cameras whose box does
-//   not fit a stage are gathered from global memory instead (same arithmetic).
+// Shared pieces of the bf16 throughput gather (gather_stream_kernel below): tile geometry, fp16 staging, packed fp32x2
+// index arithmetic.
 // ------------------------------------------------------------------------------------------------
-constexpr int GT = 8, GCELL = GT / 2, GC = GCELL + 1, GC3 = GC * GC * GC;
-#ifndef JHN_G_STAGES
-#define JHN_G_STAGES 4
-#endif
-#ifndef JHN_G_MINBLOCKS
-#define JHN_G_MINBLOCKS 3
-#endif
-constexpr int G_STAGES = JHN_G_STAGES, G_THREADS = 160;
+constexpr int GT = 8, GCELL = GT / 2, GC = GCELL + 1;                          // voxel tile side, coarse cells, corners per x / y
 constexpr int G_PIX_BYTES = KP * 2;                                           // 48 B per staged pixel
-constexpr int G_CAM_FLOATS = 2 * GC3 + 6;                                     // per camera: corners a / b, then x0 y0 bw bh|0 pitch
 
 // Packed fp32x2 arithmetic (sm_100 FMUL2 / FFMA2 / FADD2): the x and the y pixel coordinate of a corner travel
 // as one 64-bit register pair through the three nested lerps, each half an IEEE round-to-nearest fp32
@@ -419,226 +397,22 @@ template <int MODE> __device__ __forceinline__ uint64_t lerp2(uint64_t w0, uint6
     return f2_add(f2_mul(w0, a), f2_mul(w1, b));
 }
 
-template <int LAYOUT, int MODE>
-__global__ void __launch_bounds__(G_THREADS, JHN_G_MINBLOCKS)
-gather_staged_kernel(const __half *__restrict__ hm, const float2 *__restrict__ cab, int ncam,
-                     int K, int hs, int G, float post_scale, int cap_bytes, void *__restrict__ out_)
-{
-    extern __shared__ __align__(128) uint8_t gsm[];
-    uint8_t *ring = gsm;                                                       // [G_STAGES][cap_bytes] pixel boxes
-    float *cams = reinterpret_cast<float *>(gsm + (size_t)G_STAGES * cap_bytes);   // [ncam][G_CAM_FLOATS]: corners (x, y), box
-    uint64_t *bars = reinterpret_cast<uint64_t *>(cams + (size_t)ncam * G_CAM_FLOATS);
-    uint64_t *full = bars, *empty = bars + G_STAGES;
-    const int h = G / 2, nt = G / GT + 1;
-    const int b = blockIdx.y;
-    const int tk = blockIdx.x % nt, tj = (blockIdx.x / nt) % nt, ti = blockIdx.x / (nt * nt);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t nc = (size_t)h * h * h;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < G_STAGES; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // ---- one warp per camera (round robin): the tile's 5^3 coarse corners -> smem (grid indices clamped, like
-    // ATen's reads) and, in the same pass, their min / max -> the pixel box bounding every index of the tile
-    {
-        int go[4];                                                             // this lane's <= 4 corners: offset in the coarse grid
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int l = min(lane + 32 * r, GC3 - 1);
-            const int lk = l % GC, lj = (l / GC) % GC, li = l / (GC * GC);
-            const int gi = min(max(GCELL * ti - 1 + li, 0), h - 1), gj = min(max(GCELL * tj - 1 + lj, 0), h - 1),
-                      gk = min(max(GCELL * tk - 1 + lk, 0), h - 1);
-            go[r] = (gi * h + gj) * h + gk;
-        }
-        for (int c = warp; c < ncam; c += G_THREADS / 32) {
-            const float2 *src = cab + ((size_t)b * ncam + c) * nc;
-            float2 *dst = reinterpret_cast<float2 *>(cams + c * G_CAM_FLOATS);
-            float2 v[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) v[r] = __ldg(src + go[r]);
-            float amin = v[0].x, amax = v[0].x, bmin = v[0].y, bmax = v[0].y;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (lane + 32 * r < GC3) dst[lane + 32 * r] = v[r];
-                amin = fminf(amin, v[r].x); amax = fmaxf(amax, v[r].x); bmin = fminf(bmin, v[r].y); bmax = fmaxf(bmax, v[r].y);
-            }
-#pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) {
-                amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, sh)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, sh));
-                bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, sh)); bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, sh));
-            }
-            if (lane == 0) {
-                const int x0 = __float2int_rz(__fmul_rn(amin, 0.5f)), x1 = __float2int_rz(__fmul_rn(amax, 0.5f));
-                const int y0 = __float2int_rz(__fmul_rn(bmin, 0.5f)), y1 = __float2int_rz(__fmul_rn(bmax, 0.5f));
-                const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-                // smem row pitch in pixels, == 3 or 5 (mod 8): a pixel vector is three 16-byte bank groups, so two
-                // pixels collide iff their linear offsets differ by a multiple of 8; with such a pitch the short
-                // pixel runs a quarter-warp (8 voxels along z) touches almost never do
-                int pitch = bw;
-                while ((pitch & 7) != 3 && (pitch & 7) != 5) ++pitch;
-                const bool fits = pitch * bh * G_PIX_BYTES <= cap_bytes && x0 >= 0 && y0 >= 0 && x1 < hs && y1 < hs;
-                int *mi = reinterpret_cast<int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-                // byte offset of pixel (px, py): py * mi[4] + px * 48 + mi[5], inside the staged box or (box too large) the whole map
-                mi[0] = x0; mi[1] = y0; mi[2] = bw; mi[3] = fits ? bh : 0;
-                mi[4] = (fits ? pitch : hs) * G_PIX_BYTES; mi[5] = fits ? -(y0 * pitch + x0) * G_PIX_BYTES : 0;
-            }
-        }
-    }
-    __syncthreads();
-
-    if (warp == 4) {
-        // =================================== producer ========================================
-        for (int c = 0; c < ncam; ++c) {
-            const int s = c % G_STAGES;
-            if (c >= G_STAGES) mbar_wait(smem_u32(empty + s), (uint32_t)((c / G_STAGES) - 1) & 1u);
-            const int *mi = reinterpret_cast<const int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-            const int x0 = mi[0], y0 = mi[1], bw = mi[2], bh = mi[3], rowB = mi[4];
-            const uint32_t fb = smem_u32(full + s);
-            if (bh == 0) {                                                     // box does not fit: gathered from global memory
-                if (lane == 0) mbar_arrive(fb);
-                continue;
-            }
-            const uint32_t row_bytes = (uint32_t)(bw * G_PIX_BYTES);
-            if (lane == 0) mbar_expect_tx(fb, row_bytes * (uint32_t)bh);
-            __syncwarp();
-            uint8_t *box = ring + (size_t)s * cap_bytes;
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(hm) + ((((size_t)b * ncam + c) * hs + y0) * hs + x0) * G_PIX_BYTES;
-            for (int r = lane; r < bh; r += 32)
-                bulk_load(smem_u32(box + (size_t)r * rowB), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
-        }
-        return;
-    }
-
-    // =================================== gather warps ========================================
-    const int ci = warp, cj = lane >> 3, ck = (lane >> 1) & 3, kv = lane & 1;
-    const int I0 = GT * ti - 1 + 2 * ci, J0 = GT * tj - 1 + 2 * cj, Kz = GT * tk - 1 + 2 * ck + kv;
-    // ATen area_pixel_compute_source_index, scale .5: odd fine index -> lambda1 .25, even -> .75, index 0 -> 0
-    const float lk1 = Kz == 0 ? 0.f : (kv ? 0.75f : 0.25f), lk0 = __fsub_rn(1.f, lk1);
-    const uint64_t wk0 = f2_pack(lk0, lk0), wk1 = f2_pack(lk1, lk1), whalf = f2_pack(0.5f, 0.5f);
-    uint64_t wj1[2], wj0[2], wi1[2], wi0[2];
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-        const float j1 = (J0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f), j0 = __fsub_rn(1.f, j1);
-        const float i1 = (I0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f), i0 = __fsub_rn(1.f, i1);
-        wj1[v] = f2_pack(j1, j1); wj0[v] = f2_pack(j0, j0); wi1[v] = f2_pack(i1, i1); wi0[v] = f2_pack(i0, i0);
-    }
-    __half2 acc[4][KP / 2];
-#pragma unroll
-    for (int v = 0; v < 4; ++v)
-#pragma unroll
-        for (int i = 0; i < KP / 2; ++i) acc[v][i] = __float2half2_rn(0.f);
-    const int l0 = (ci * GC + cj) * GC + ck;
-
-    for (int c = 0; c < ncam; ++c) {
-        const int s = c % G_STAGES;
-        const uint64_t *Cn = reinterpret_cast<const uint64_t *>(cams + c * G_CAM_FLOATS) + l0;      // (x, y) corner pairs
-        const int *mi = reinterpret_cast<const int *>(cams + c * G_CAM_FLOATS + 2 * GC3);
-        const int fits = mi[3], rowB = mi[4], baseB = mi[5];
-        // indices of this thread's four voxels (registers only; same arithmetic as gather_fused_kernel phase A)
-        uint64_t xk[2][2];
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int l = (p * GC + q) * GC;
-                xk[p][q] = lerp2<MODE>(wk0, Cn[l], wk1, Cn[l + 1]);
-            }
-        int off[4];
-#pragma unroll
-        for (int jv = 0; jv < 2; ++jv) {
-            uint64_t yj[2];
-#pragma unroll
-            for (int p = 0; p < 2; ++p) yj[p] = lerp2<MODE>(wj0[jv], xk[p][0], wj1[jv], xk[p][1]);
-#pragma unroll
-            for (int iv = 0; iv < 2; ++iv) {
-                float fa, fb2;
-                f2_unpack(f2_mul(lerp2<MODE>(wi0[iv], yj[0], wi1[iv], yj[1]), whalf), fa, fb2);
-                const int px = __float2int_rz(fa), py = __float2int_rz(fb2);                        // (val/2).int()   repro_layer.py:82-83
-                off[iv * 2 + jv] = py * rowB + (px * G_PIX_BYTES + baseB);
-            }
-        }
-        mbar_wait(smem_u32(full + s), (uint32_t)(c / G_STAGES) & 1u);
-        uint4 w[4][3];
-        if (fits) {
-            const uint8_t *box = ring + (size_t)s * cap_bytes;
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const uint4 *pp = reinterpret_cast<const uint4 *>(box + off[v]);
-                w[v][0] = pp[0]; w[v][1] = pp[1]; w[v][2] = pp[2];
-            }
-        } else {
-            const uint8_t *gbase = reinterpret_cast<const uint8_t *>(hm) + ((size_t)b * ncam + c) * hs * hs * G_PIX_BYTES;
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const uint4 *pp = reinterpret_cast<const uint4 *>(gbase + off[v]);
-                w[v][0] = __ldg(pp); w[v][1] = __ldg(pp + 1); w[v][2] = __ldg(pp + 2);
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                const uint32_t ww[4] = {w[v][g].x, w[v][g].y, w[v][g].z, w[v][g].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[v][4 * g + i] = __hadd2(acc[v][4 * g + i], *reinterpret_cast<const __half2 *>(&ww[i]));
-            }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(empty + s));
-    }
-
-    // ---- mean over cameras (+ /255) as one fp32 scale, store ---------------------------------------
-    const size_t nv = (size_t)G * G * G;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const int I = I0 + (v >> 1), J = J0 + (v & 1);
-        if (I < 0 || J < 0 || Kz < 0 || I >= G || J >= G || Kz >= G) continue;
-        float m[KP];
-#pragma unroll
-        for (int i = 0; i < KP / 2; ++i) {
-            const float2 f = __half22float2(acc[v][i]);
-            m[2 * i] = f.x * post_scale; m[2 * i + 1] = f.y * post_scale;
-        }
-        if (LAYOUT == JHN_VOL_NCDHW_F32) {
-            float *out = (float *)out_ + (size_t)b * K * nv + ((size_t)I * G + J) * G + Kz;
-#pragma unroll
-            for (int k = 0; k < KP; ++k)
-                if (k < K) out[(size_t)k * nv] = m[k];
-        } else {
-            const int CJ = (K + 15) / 16 * 2, Wh = G / 2 + 2;
-            const int sv = ((I & 1) * 2 + (J & 1)) * 2 + (Kz & 1);
-            uint4 *out = (uint4 *)out_;
-            const size_t pos = ((size_t)(I >> 1) + 1) * Wh * Wh + (size_t)((J >> 1) + 1) * Wh + (Kz >> 1) + 1;
-            const size_t chunk_stride = (size_t)Wh * Wh * Wh;
-            const size_t ob = (((size_t)b * 8 + sv) * CJ) * chunk_stride + pos;
-#pragma unroll
-            for (int j = 0; j < KP / 8; ++j) {
-                if (j < CJ) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(m[8 * j + 2 * i], m[8 * j + 2 * i + 1]);
-                        pk[i] = *reinterpret_cast<uint32_t *>(&h2);
-                    }
-                    out[ob + (size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
-            }
-            for (int jz = KP / 8; jz < CJ; ++jz) out[ob + (size_t)jz * chunk_stride] = make_uint4(0, 0, 0, 0);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Streaming gather: the staged gather as a persistent, software-pipelined kernel.  ncu of the one-tile-per-CTA
-// kernel above showed every CTA paying the chain  corner LDG -> box -> TMA -> first LDS  (~13 us per tile against
-// ~1 us of issue work), 27 % of the lanes parked on voxels outside the grid, and the LSU-shared pipe at 55 %.
-// Here a CTA walks tiles blockIdx.x, +gridDim.x, ... and the producer warp runs ahead of the gather warps across
-// tile boundaries through two rings: a deep one of small headers [150 (x, y) corner pairs | pixel box] and a
-// shallow one of pixel boxes.
-//   producer, item n:      wait header slot -> 150 x cp.async (LDGSTS, 8 B) corners into header n
-//             item n - D:  cp.async.wait_group -> own corners back -> integer min / max (REDUX) -> box -> wait box slot ->
-//                          mbarrier.arrive.expect_tx -> one cp.async.bulk per box row
-//   gather warps:          wait full -> corners + box meta -> indices -> LDS.128 -> HADD2 -> arrive both empties
+// Streaming gather.  One work item = (8x8x8 voxel tile, camera).  The tile's fine coordinates are lerps of 5x5x6
+// coarse corners, so every index of the item falls inside the pixel box spanned by the corners: the box (~140
+// pixels x 48 B) is staged in shared memory by TMA and each (voxel, camera) gather is three LDS.128.
+//
+// An earlier one-tile-per-CTA version of this kernel (profiles/r01_run25) paid the chain  corner LDG -> box -> TMA ->
+// first LDS  once per CTA (~13 us per tile against ~1 us of issue work) and parked 27 % of its lanes on voxels
+// outside the grid.  Here CTAs are persistent (3 per SM, tiles blockIdx.x, +gridDim.x, ...) and warp-specialised:
+//   4 producer warps (setmaxnreg 40), producer p owning box slot p and items p, p + 4, ... of the CTA's sequence:
+//       corners of the item: 150 x cp.async (LDGSTS, 8 B) into the item's header, issued one item ahead
+//       cp.async.wait_group -> integer min / max of the corners' pixels (REDUX) = the box -> smem row pitch chosen
+//       for few bank conflicts -> wait for the slot -> mbarrier.arrive.expect_tx -> one cp.async.bulk per box row
+//     (one producer warp cannot keep up: its dependent chain is ~2 us per item; four run their chains in parallel)
+//   4 gather warps (setmaxnreg 120), thread = 2x2 voxels (x, y) at one z sharing the separable lerps:
+//       wait full -> 8 corner pairs -> nested fp32x2 lerps -> F2I -> 12 x LDS.128 -> 48 x HADD2 -> arrive empty;
+//       after the last camera: one fp32 scale, bf16 pack, 16-byte stores into the first convolution's input layout.
 // z tiles are unshifted (6 corners along z instead of 5) so that no lane is ever outside the grid along z;
 // along x / y whole warps / quarter-warps outside the grid skip the step (no LSU wavefronts).
 // ------------------------------------------------------------------------------------------------
@@ -934,29 +708,6 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
     }
 }
 
-template <int LAYOUT>
-static int launch_staged(const ReprojectArgs &a, const __half *hm_cl, const float2 *cab, int cap, cudaStream_t st)
-{
-    const size_t gsmem = (size_t)G_STAGES * cap + (size_t)a.ncam * G_CAM_FLOATS * 4 + 2 * G_STAGES * 8;
-    if (gsmem > 200 * 1024) return fail(JHN_ERR_SHAPE, "too many cameras (%d) for the staged gather", a.ncam);
-    const int nt = a.G / GT + 1;
-    dim3 grid(nt * nt * nt, a.B);
-    // the bf16 volume hides a 1-ulp difference between x/ncam/post_divide and x*(1/(ncam*post_divide)); 16 undoes the fp16 pre-scale
-    const float post_scale = HALF_STAGE_UNSCALE / ((float)a.ncam * a.post_divide);
-#define JHN_STAGED(MODE)                                                                                         \
-    {                                                                                                            \
-        auto kern = gather_staged_kernel<LAYOUT, MODE>;                                                          \
-        JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));           \
-        JHN_LAUNCH("gather_staged_kernel", st,                                                                   \
-                   kern<<<grid, G_THREADS, gsmem, st>>>(hm_cl, cab, a.ncam, a.K, a.hs, a.G, post_scale, cap, a.volume_out)); \
-        return JHN_OK;                                                                                           \
-    }
-    if (a.lerp_mode == JHN_LERP_FMA_FIRST) JHN_STAGED(JHN_LERP_FMA_FIRST)
-    if (a.lerp_mode == JHN_LERP_FMA_SECOND) JHN_STAGED(JHN_LERP_FMA_SECOND)
-    JHN_STAGED(JHN_LERP_NO_FMA)
-#undef JHN_STAGED
-}
-
 constexpr int GS_CAP = 15360;                                                  // bytes per pixel-box slot of the streaming kernel
 static int g_box_limit = GS_CAP;                                               // boxes above this gather from global memory (test hook)
 int gather_set_box_bytes(int bytes)
@@ -996,7 +747,6 @@ static int launch_stream(const ReprojectArgs &a, const __half *hm_cl, const floa
 #undef JHN_STREAM
 }
 
-static int pick_gather_cap(int) { return 12288; }                             // bytes of pixel box per ring stage (staged kernel)
 
 size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
 {
@@ -1052,24 +802,19 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
         return run_gather<float>(a, (const float *)hm_cl, cab, st);
     }
     if (!a.index_out && a.G % GT == 0) {
-        // throughput path: fp16 staging copy + staged gather (the index dump needs the in-order kernel below)
+        // throughput path: fp16 staging copy + streaming gather (the index dump needs the in-order kernel below)
         JHN_TRY(launch_relayout<__half>(a, (__half *)hm_cl, st));
-        const int cap = pick_gather_cap(a.hs);
-        static const int use_staged = getenv("JHN_GATHER_STAGED") != nullptr;         // A/B switch: the one-tile-per-CTA kernel
-        if (a.layout == JHN_VOL_NCDHW_F32)
-            return use_staged ? launch_staged<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, cap, st)
-                              : launch_stream<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, GS_CAP, st);
+        if (a.layout == JHN_VOL_NCDHW_F32) return launch_stream<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, GS_CAP, st);
         const int CJ = (a.K + 15) / 16 * 2;
         if (!a.borders_valid) {
             JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
-            if (!use_staged && CJ > KP / 8) {                                  // all-padding channel chunks: zeroed here, never written by the kernel
+            if (CJ > KP / 8) {                                                 // all-padding channel chunks: zeroed here, never written by the kernel
                 const size_t Wh = a.G / 2 + 2, chunk_bytes = Wh * Wh * Wh * 16;
                 JHN_CUDA(cudaMemset2DAsync((char *)a.volume_out + (KP / 8) * chunk_bytes, CJ * chunk_bytes, 0,
                                            (CJ - KP / 8) * chunk_bytes, (size_t)a.B * 8, st));
             }
         }
-        return use_staged ? launch_staged<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, cap, st)
-                          : launch_stream<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, GS_CAP, st);
+        return launch_stream<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, GS_CAP, st);
     }
     JHN_TRY(launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)hm_cl, st));
     return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, cab, st);
