@@ -77,17 +77,22 @@ struct TcLaunch {
 constexpr int TC_THREADS = 320;                      // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int TC_EPI_WARPS = 8;
 constexpr int EPI_TILE_FLOATS = 32 * 17;
-constexpr int MAX_DESC = 768;                         // descriptor pairs: (MMAs per tile) x (ring slots)
-constexpr int TC_SMEM_TAIL = TC_EPI_WARPS * EPI_TILE_FLOATS * 4 + 128 * 4 + 30 * 8 + MAX_DESC * 8 + 1024;
+constexpr int TC_MAX_SLOTS = 16;                       // ring depth: bytes in flight per SM = slots x box; 8 slots of the
+                                                      // 10 KB front-conv boxes cover only ~2/3 of the L2 latency-bandwidth product
+constexpr int MAX_DESC = 1024;                         // descriptor pairs: (MMAs per tile) x (ring slots)
+constexpr int TC_SMEM_TAIL = TC_EPI_WARPS * EPI_TILE_FLOATS * 4 + 128 * 4 + (2 * TC_MAX_SLOTS + 14) * 8 + MAX_DESC * 8 + 1024;
 
 struct TileCoord { int b, z, pt, tap; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const TcLaunch &L, int tile_taps)
 {
     TileCoord c;
+    // z fastest: consecutive tiles of a CTA's range share their in-plane position, so the input planes a tile
+    // re-reads for z + 1 were fetched one tile ago and are still in L2 (with the in-plane index fastest the reuse
+    // distance was a whole plane of tiles, more than a CTA's share of L2)
     c.tap = t % tile_taps; t /= tile_taps;
-    c.pt = t % L.NT; t /= L.NT;
-    c.z = t % L.D;
-    c.b = t / L.D;
+    c.z = t % L.D; t /= L.D;
+    c.pt = t % L.NT;
+    c.b = t / L.NT;
     return c;
 }
 
@@ -105,10 +110,10 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
     float *epi_tiles = reinterpret_cast<float *>(ring + (size_t)P.nslots * P.stage_bytes);
     float *bias_s = epi_tiles + TC_EPI_WARPS * EPI_TILE_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 128);
-    uint64_t *full = bars, *empty = bars + 8, *tfull = bars + 16, *tempty = bars + 18, *wbar = bars + 20;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
-    int *stage_first = reinterpret_cast<int *>(bars + 22);            // [MAX_STAGES + 1]
-    uint2 *desc_list = reinterpret_cast<uint2 *>(bars + 30);          // [nslots][MMAs per tile] (A desc lo, B desc lo)
+    uint64_t *full = bars, *empty = bars + TC_MAX_SLOTS, *tfull = bars + 2 * TC_MAX_SLOTS, *tempty = tfull + 2, *wbar = tfull + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfull + 5);
+    int *stage_first = reinterpret_cast<int *>(tfull + 6);            // [MAX_STAGES + 1]
+    uint2 *desc_list = reinterpret_cast<uint2 *>(tfull + 14);         // [nslots][MMAs per tile] (A desc lo, B desc lo)
 
     // contiguous tile range of this CTA
     const int t_begin = (int)((long long)L.total_tiles * blockIdx.x / gridDim.x);
@@ -683,7 +688,7 @@ static int build_program(TcProgram &P, int kind, int cin_pad, int cout_pad, int 
     P.w_bytes = P.resident ? (int)align_up((size_t)P.ntaps_total * tap_bytes, 128) : 0;
     const int fixed = P.w_bytes + TC_SMEM_TAIL;
     int slots = (max_smem - fixed) / P.stage_bytes;
-    if (slots > 8) slots = 8;
+    if (slots > TC_MAX_SLOTS) slots = TC_MAX_SLOTS;
     int n_mma = 0;
     for (int s = 0; s < P.nstages; ++s) n_mma += P.st[s].ntaps * (P.KC / 2);
     while (slots > 2 && slots * n_mma > MAX_DESC) --slots;

@@ -170,38 +170,51 @@ __device__ __forceinline__ void add8(const __nv_bfloat16 *p, float *acc)
     }
 }
 
-// planar -> channels-last without shared memory: one thread per padded pixel reads its K channel values (for a
-// fixed channel the lanes of a warp read consecutive floats: coalesced, K independent loads in flight per
-// thread) and writes the KP-vector as 16-byte stores; the three / six stores of a warp fill whole lines in L2.
+// planar -> channels-last: one thread per padded pixel reads its K channel values (for a fixed channel the lanes
+// of a warp read consecutive floats: coalesced, K independent loads in flight per thread); the 16-bit staging
+// copy goes through a per-warp shared-memory tile so that each store instruction writes 512 contiguous bytes.
 template <typename T>
 __global__ void __launch_bounds__(256)
 relayout_pixel_kernel(const float *__restrict__ in, int K, int hs, int padded, long long npix, T *__restrict__ out)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= npix) return;
+    const bool live = idx < npix;                                    // lanes past the end stay for the warp-wide staging below
     const int hh = hs * hs;
-    const long long bc = idx / hh;
-    const int r = (int)(idx - bc * hh), y = r / hs, x = r - y * hs;
+    const long long bc = (live ? idx : 0) / hh;
+    const int r = (int)((live ? idx : 0) - bc * hh), y = r / hs, x = r - y * hs;
     const int S = padded ? hs : hs - 2, off = padded ? 0 : 1;
     const int ys = y - off, xs = x - off;
-    const bool inside = ys >= 0 && ys < S && xs >= 0 && xs < S;
+    const bool inside = live && ys >= 0 && ys < S && xs >= 0 && xs < S;
     float v[KP];
     const float *src = in + ((size_t)bc * K * S + (inside ? ys : 0)) * S + (inside ? xs : 0);
 #pragma unroll
     for (int k = 0; k < KP; ++k) v[k] = (inside && k < K) ? __ldg(src + (size_t)k * S * S) : 0.f;
-    T *dst = out + (size_t)idx * KP;
     if (sizeof(T) == 4) {
+        if (!live) return;
+        T *dst = out + (size_t)idx * KP;
 #pragma unroll
         for (int i = 0; i < KP / 4; ++i)
             reinterpret_cast<float4 *>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     } else {
+        // 16-bit staging: a warp's 32 pixel vectors are 1536 contiguous bytes; pass them through shared memory so that
+        // every store instruction writes 512 contiguous bytes instead of 32 x 16 B at a 48-byte stride
+        __shared__ __align__(16) uint4 stage[256 / 32][32 * (KP / 8)];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
         for (int i = 0; i < KP / 8; ++i) {
             T t[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) t[j] = to_store<T>(v[8 * i + j]);
-            reinterpret_cast<uint4 *>(dst)[i] = *reinterpret_cast<const uint4 *>(t);
+            stage[warp][lane * (KP / 8) + i] = *reinterpret_cast<const uint4 *>(t);
         }
+        __syncwarp();
+        const long long first = idx - lane;                          // the warp's first pixel
+        if (first >= npix) return;
+        uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)first * KP);
+        const long long n16 = (npix - first) * (KP / 8);             // 16-byte units left in the tensor from `first`
+#pragma unroll
+        for (int i = 0; i < KP / 8; ++i)
+            if (i * 32 + lane < n16) dst[i * 32 + lane] = stage[warp][i * 32 + lane];
     }
 }
 
