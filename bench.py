@@ -302,6 +302,8 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
     ap.add_argument("--ref-sample", type=int, default=2, help="frame sets per reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--job-frame-sets", type=int, default=0,
+                    help="also run one sharded job of this many frame sets with a single gather at the end (BASELINE configs[3]: 100000)")
     ap.add_argument("--no-latency", action="store_true", help="skip the B=1 eager / CUDA-graph latency measurement")
     args = ap.parse_args()
     claim_stdout()
@@ -419,6 +421,33 @@ def main():
         torch.cuda.synchronize(); gather_ms = 1e3 * (time.perf_counter() - g0)
         assert full.shape[0] == world * B
 
+    # ---- BASELINE.json configs[3]: one sharded job of N frame sets, outputs gathered once at the end -----------
+    job = None
+    if args.job_frame_sets > 0:
+        from jarvis_hybridnet_b200 import shard_range
+        N = args.job_frame_sets
+        lo, hi = shard_range(N, rank, world)
+        local_res = torch.empty((hi - lo, sh.K, 4), dtype=torch.float32, device="cuda")
+        barrier()
+        j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        j0.record()
+        done, i = 0, 0
+        while done < hi - lo:
+            nb = min(B, hi - lo - done)
+            pts, conf, _ = net(*[t[:nb] for t in devb[i % n_pool]])
+            local_res[done:done + nb, :, :3] = pts
+            local_res[done:done + nb, :, 3] = conf
+            done += nb; i += 1
+        full = gather_results(local_res, N) if world > 1 else local_res
+        j1.record()
+        barrier()
+        tj = torch.tensor([j0.elapsed_time(j1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(tj, op=dist.ReduceOp.MAX)
+        assert full.shape[0] == N and bool(torch.isfinite(full).all())
+        job = dict(frame_sets=N, ms=float(tj.item()), frame_sets_per_sec=N / (float(tj.item()) * 1e-3), steps_per_rank=i,
+                   note="contiguous shard per rank, %d frame sets per step, one all-gather of [N,K,4] inside the timed region" % B)
+
     # ---- per-kernel device time (CUDA events inside the library) over the same steps ---------------
     _lib.profile(True)
     for i in range(K_steps):
@@ -486,7 +515,7 @@ def main():
                                 l2="inputs rotate through %d batches of %.0f MB (>> 126 MB L2)" % (n_pool, B * sh.ncam * sh.K * sh.hm ** 2 * 4 / 1e6),
                                 timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded"),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb,
-                    stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms, latency_b1=latency)
+                    stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms, latency_b1=latency, job=job)
         emit(line)
     if world > 1:
         dist.barrier()
