@@ -154,6 +154,22 @@ def test_streaming_gather_batched_equals_single():
         assert torch.equal(one[0], vol[b]), b
 
 
+@pytest.mark.parametrize("ncam", [1, 3, 5])
+def test_streaming_gather_odd_camera_counts(oracle, ncam):
+    """Camera counts below / not a multiple of the number of producer warps (items = tile x camera are dealt round
+    robin to four producers): no producer may be left waiting, results as the oracle's."""
+    from jarvis_hybridnet_b200 import ReprojectionLayer
+    import jarvis_hybridnet_b200.synth as S
+    sh = S.Shape3D(ncam, 5, 64, 48, 2)
+    cam, intr, dist = S.make_rig(ncam, 21)
+    hm, c3, chm, _ = S.make_frameset(sh, cam, intr, dist, 4)
+    L = ReprojectionLayer(cfg_of(sh), precision="bf16")
+    x = dict(hm=hm, c3=c3, chm=chm, cam=cam, intr=intr, dist=dist)
+    vol, _ = L.forward_batched(*repro_inputs(x), post_divide=255.0, want_index=False)
+    want, _ = oracle.repro_layer_forward(oracle.pad_heatmaps(hm), c3, chm, cam, intr, dist, sh.G, sh.spacing)
+    np.testing.assert_allclose(vol[0].cpu().numpy(), want / 255.0, rtol=2e-2, atol=2e-2 * 4 / 255)
+
+
 def test_batched_equals_single(oracle):
     """B frame sets in one launch == B reference-style B=1 forwards."""
     from jarvis_hybridnet_b200 import ReprojectionLayer
