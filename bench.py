@@ -104,6 +104,24 @@ def make_inputs(sh, batch, n_batches, seed=0, distinct=8):
     return batches, sets, (cam, intr, dist)
 
 
+def roi_fraction(sh, sets, rig):
+    """Share of a padded heat map inside the camera's pixel box of the voxel grid (what the staging copy converts):
+    the 8 corners of the coarse grid projected with synth.project, +-1 px, averaged over the frame sets and cameras."""
+    cam, intr, dist = rig
+    hs, fr = sh.hs, []
+    lo, hi = -sh.roi / 2.0, sh.roi / 2.0 - 2 * sh.spacing
+    for hm, c3, chm, _ in sets:
+        corners = np.array([[x, y, z] for x in (lo, hi) for y in (lo, hi) for z in (lo, hi)], np.float64) + c3.astype(np.float64)
+        px = S.project(corners, cam, intr, dist)                                  # [ncam,8,2] full-resolution pixels
+        a = np.clip(px - chm[:, None, :] + hs - 1, 0, 2 * hs - 3) / 2.0
+        x0, x1 = np.floor(a[..., 0].min(1)) - 1, np.floor(a[..., 0].max(1)) + 1
+        y0, y1 = np.floor(a[..., 1].min(1)) - 1, np.floor(a[..., 1].max(1)) + 1
+        w = np.clip(x1, 0, hs - 1) - np.clip(x0, 0, hs - 1) + 1
+        h = np.clip(y1, 0, hs - 1) - np.clip(y0, 0, hs - 1) + 1
+        fr.append(float((w * h).mean()) / (hs * hs))
+    return float(np.mean(fr))
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -458,6 +476,7 @@ def main():
     fl = v2v_flops(sh)
     kern = {k: dict(launches=n, ms_per_step=msk / K_steps) for k, (n, msk) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
     s_in, s_vol = 4, (4 if precision == "fp32" else 2)
+    roi = roi_fraction(sh, sets, rig)
     REPRO = ("coarse_project_kernel", "fine_index_kernel", "relayout_kernel", "gather_mean_kernel", "gather_fused_kernel",
              "gather_staged_kernel", "gather_stream_kernel")
     rp_ms = sum(v["ms_per_step"] for k, v in kern.items() if k in REPRO)
@@ -477,7 +496,8 @@ def main():
                 "tc_conv_head_1x1": fl["head_1x1"], "conv3d_f32_kernel<3>": fl["front_k3s2"] + fl["res_k3_2C"] + fl["res_k3_4C"]}
     byte_fam = {"gather_staged_kernel": B * repro_bytes(sh, 2, s_vol), "gather_stream_kernel": B * repro_bytes(sh, 2, s_vol), "gather_fused_kernel": B * repro_bytes(sh, s_vol, s_vol),
                 "gather_mean_kernel": B * repro_bytes(sh, s_vol, s_vol),
-                "relayout_kernel": B * sh.ncam * K * sh.hm ** 2 * (s_in + s_vol),
+                # the bf16 path converts only each camera's pixel box of the voxel grid (share `roi` of the padded map)
+                "relayout_kernel": B * sh.ncam * K * (sh.hm ** 2 if precision == "fp32" else roi * sh.hs ** 2) * (s_in + s_vol),
                 "coarse_project_kernel": B * sh.ncam * h ** 3 * 8,
                 "tc_head_centroid_kernel": act(2 * K, h), "centroid_kernel": B * K * h ** 3 * 4,
                 # 5 plain + 1 residual + 1 residual/PS-copy + 1 residual/skip on the h grid, 2 plain + 1 residual on the q grid
@@ -513,7 +533,8 @@ def main():
                     config=dict(workload=args.workload, ncam=sh.ncam, K=sh.K, heatmap=sh.hm, grid=sh.G,
                                 frame_sets_per_step_per_gpu=B, weights="random-init he (seed 0)",
                                 l2="inputs rotate through %d batches of %.0f MB (>> 126 MB L2)" % (n_pool, B * sh.ncam * sh.K * sh.hm ** 2 * 4 / 1e6),
-                                timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded"),
+                                timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded",
+                                roi_share_of_heatmap=roi),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb,
                     stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms, latency_b1=latency, job=job)
         emit(line)

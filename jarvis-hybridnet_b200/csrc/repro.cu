@@ -13,7 +13,8 @@
 //                          expression because every intermediate is an fp32 value in both).  The indices
 //                          live in shared memory only (the reference materialises them as a 36 MB int64
 //                          tensor); they are written to HBM only when the caller asks for the parity dump.
-//   relayout_kernel        [ncam][K][S][S] planar fp32 -> channels-last [ncam][hs][hs][KP] (fp32 or bf16)
+//   relayout_kernel        [ncam][K][S][S] planar fp32 -> channels-last [ncam][hs][hs][KP] (fp32, bf16 or fp16;
+//                          the fp16 copy of the streaming gather only inside each camera's pixel box of the grid)
 //                          with the 1-px zero border of F.pad materialised, so that one voxel x camera
 //                          gather is a single contiguous KP-vector instead of K strided scalars.
 //   gather_fused_kernel    (fp32 parity path, and whenever the int32 index dump is requested) per 8x8x8 voxel
@@ -45,9 +46,12 @@ __global__ void __launch_bounds__(256)
 coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ intr,
                       const float *__restrict__ dist, const int32_t *__restrict__ center3D,
                       const int32_t *__restrict__ centerHM, int B, int ncam, int h, float spacing, int hs,
-                      float2 *__restrict__ cab)
+                      float2 *__restrict__ cab, int *__restrict__ roi)
 {
-    extern __shared__ float cp[];                       // [ncam][CP_PARAMS]
+    extern __shared__ float cp[];                       // [ncam][CP_PARAMS], then (roi != null) int [ncam][4] block-level box
+    int *sbox = reinterpret_cast<int *>(cp + ncam * CP_PARAMS);
+    if (roi)
+        for (int e = threadIdx.x; e < ncam * 4; e += blockDim.x) sbox[e] = 0x7f7f7f7f;
     const int b = blockIdx.y;
     for (int e = threadIdx.x; e < ncam * CP_PARAMS; e += blockDim.x) {
         const int c = e / CP_PARAMS, q = e - c * CP_PARAMS, bc = b * ncam + c;
@@ -64,8 +68,9 @@ coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ i
     }
     __syncthreads();
     const int nc = h * h * h;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nc) return;
+    const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = tt < nc;
+    const int t = live ? tt : nc - 1;                   // lanes past the end repeat the last point (they only feed the box)
     const int k = t % h, j = (t / h) % h, i = t / (h * h);
     const int half = h / 2;
     const float fhs = (float)hs, fhs1 = (float)(hs - 1), fhs2 = (float)(hs - 2);
@@ -101,7 +106,23 @@ coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ i
         bb = fminf(fmaxf(bb, loy), hiy);                                                      // :67-68
         bb = __fsub_rn(__fadd_rn(__fsub_rn(bb, chy), fhs), 1.f);
         const size_t o = ((size_t)b * ncam + c) * nc + t;
-        cab[o] = make_float2(a, bb);                         // (x, y) interleaved: one 8-byte access per corner downstream
+        if (live) cab[o] = make_float2(a, bb);               // (x, y) interleaved: one 8-byte access per corner downstream
+        if (roi) {
+            // pixel box of this camera over the whole voxel grid = min / max over all coarse corners (the fine coordinates
+            // are rounded convex combinations of them): warp REDUX -> shared atomics -> one global atomic per block.
+            // Stored as {x0, y0, -x1, -y1} so that all four are minima of a buffer memset to 0x7f7f7f7f.
+            const int px = __float2int_rz(__fmul_rn(a, 0.5f)), py = __float2int_rz(__fmul_rn(bb, 0.5f));
+            const int x0 = __reduce_min_sync(0xffffffffu, px), y0 = __reduce_min_sync(0xffffffffu, py);
+            const int x1 = __reduce_max_sync(0xffffffffu, px), y1 = __reduce_max_sync(0xffffffffu, py);
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(sbox + 4 * c + 0, x0); atomicMin(sbox + 4 * c + 1, y0);
+                atomicMin(sbox + 4 * c + 2, -x1); atomicMin(sbox + 4 * c + 3, -y1);
+            }
+        }
+    }
+    if (roi) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < ncam * 4; e += blockDim.x) atomicMin(roi + ((size_t)b * ncam) * 4 + e, sbox[e]);
     }
 }
 
@@ -175,13 +196,21 @@ __device__ __forceinline__ void add8(const __nv_bfloat16 *p, float *acc)
 // copy goes through a per-warp shared-memory tile so that each store instruction writes 512 contiguous bytes.
 template <typename T>
 __global__ void __launch_bounds__(256)
-relayout_pixel_kernel(const float *__restrict__ in, int K, int hs, int padded, long long npix, T *__restrict__ out)
+relayout_pixel_kernel(const float *__restrict__ in, int K, int hs, int padded, long long npix, const int4 *__restrict__ roi,
+                      T *__restrict__ out)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = idx < npix;                                    // lanes past the end stay for the warp-wide staging below
     const int hh = hs * hs;
     const long long bc = (live ? idx : 0) / hh;
     const int r = (int)((live ? idx : 0) - bc * hh), y = r / hs, x = r - y * hs;
+    if (roi) {
+        // only the pixels the gather can touch: the camera's box over the whole voxel grid (coarse_project_kernel); whole warps
+        // outside it leave without a load or a store (their part of the staging copy is never read)
+        const int4 bx = __ldg(roi + bc);
+        const bool hit = live && x >= bx.x && x <= -bx.z && y >= bx.y && y <= -bx.w;        // {x0, y0, -x1, -y1}
+        if (!__any_sync(0xffffffffu, hit)) return;
+    }
     const int S = padded ? hs : hs - 2, off = padded ? 0 : 1;
     const int ys = y - off, xs = x - off;
     const bool inside = live && ys >= 0 && ys < S && xs >= 0 && xs < S;
@@ -219,11 +248,11 @@ relayout_pixel_kernel(const float *__restrict__ in, int K, int hs, int padded, l
 }
 
 template <typename T>
-static int launch_relayout(const ReprojectArgs &a, T *hm_cl, cudaStream_t st)
+static int launch_relayout(const ReprojectArgs &a, T *hm_cl, const int4 *roi, cudaStream_t st)
 {
     const long long npix = (long long)a.B * a.ncam * a.hs * a.hs;
     JHN_LAUNCH("relayout_kernel", st,
-               relayout_pixel_kernel<T><<<cdiv(npix, 256), 256, 0, st>>>(a.heatmaps, a.K, a.hs, a.padded, npix, hm_cl));
+               relayout_pixel_kernel<T><<<cdiv(npix, 256), 256, 0, st>>>(a.heatmaps, a.K, a.hs, a.padded, npix, roi, hm_cl));
     return JHN_OK;
 }
 
@@ -768,6 +797,7 @@ size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
     a.take<float2>((size_t)B * ncam * h * h * h);                   // coarse (x, y) pixel coordinates
     const size_t px = (size_t)B * ncam * hs * hs * KP;
     if (precision == JHN_FP32) a.take<float>(px); else a.take<__nv_bfloat16>(px);
+    a.take<int4>((size_t)B * ncam);                                 // per-camera pixel box of the voxel grid
     return a.off;
 }
 
@@ -805,18 +835,24 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
     float2 *cab = ar.take<float2>((size_t)a.B * a.ncam * h * h * h);
     const size_t px = (size_t)a.B * a.ncam * a.hs * a.hs * KP;
     void *hm_cl = (a.precision == JHN_FP32) ? (void *)ar.take<float>(px) : (void *)ar.take<__nv_bfloat16>(px);
+    int4 *roi = ar.take<int4>((size_t)a.B * a.ncam);
     if (!ar.ok()) return fail(JHN_ERR_WORKSPACE, "reproject workspace: need %zu bytes, got %zu", ar.off, ws_bytes);
 
+    // the streaming gather's staging copy covers only each camera's pixel box of the voxel grid (collected by the
+    // projection kernel); the other paths relayout whole maps
+    const bool stream = a.precision != JHN_FP32 && !a.index_out && a.G % GT == 0;
+    if (stream) JHN_CUDA(cudaMemsetAsync(roi, 0x7f, (size_t)a.B * a.ncam * sizeof(int4), st));
     JHN_LAUNCH("coarse_project_kernel", st,
-               coarse_project_kernel<<<dim3(cdiv((long long)h * h * h, 256), a.B), 256, a.ncam * CP_PARAMS * sizeof(float), st>>>(
-                   a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B, a.ncam, h, a.spacing, a.hs, cab));
+               coarse_project_kernel<<<dim3(cdiv((long long)h * h * h, 256), a.B), 256,
+                                       a.ncam * (CP_PARAMS * sizeof(float) + 4 * sizeof(int)), st>>>(
+                   a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B, a.ncam, h, a.spacing, a.hs, cab, stream ? (int *)roi : nullptr));
     if (a.precision == JHN_FP32) {
-        JHN_TRY(launch_relayout<float>(a, (float *)hm_cl, st));
+        JHN_TRY(launch_relayout<float>(a, (float *)hm_cl, nullptr, st));
         return run_gather<float>(a, (const float *)hm_cl, cab, st);
     }
-    if (!a.index_out && a.G % GT == 0) {
+    if (stream) {
         // throughput path: fp16 staging copy + streaming gather (the index dump needs the in-order kernel below)
-        JHN_TRY(launch_relayout<__half>(a, (__half *)hm_cl, st));
+        JHN_TRY(launch_relayout<__half>(a, (__half *)hm_cl, roi, st));
         if (a.layout == JHN_VOL_NCDHW_F32) return launch_stream<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, GS_CAP, st);
         const int CJ = (a.K + 15) / 16 * 2;
         if (!a.borders_valid) {
@@ -829,7 +865,7 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
         }
         return launch_stream<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, GS_CAP, st);
     }
-    JHN_TRY(launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)hm_cl, st));
+    JHN_TRY(launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)hm_cl, nullptr, st));
     return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, cab, st);
 }
 
