@@ -170,6 +170,32 @@ def test_streaming_gather_odd_camera_counts(oracle, ncam):
     np.testing.assert_allclose(vol[0].cpu().numpy(), want / 255.0, rtol=2e-2, atol=2e-2 * 4 / 255)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_streaming_gather_random_shapes(oracle, seed):
+    """Random small shapes (camera count, key points, map size, grid side, spacing, frame sets per call) and crop
+    centres shifted so that part of the grid clamps at the map border: streaming gather vs the oracle's fp32 gather."""
+    from jarvis_hybridnet_b200 import ReprojectionLayer
+    import jarvis_hybridnet_b200.synth as S
+    rng = np.random.default_rng(100 + seed)
+    ncam, K = int(rng.integers(1, 9)), int(rng.integers(1, 25))
+    bbox = int(rng.choice([32, 64, 96, 128]))
+    spacing = int(rng.choice([1, 2, 3]))
+    G = int(rng.choice([8, 16, 24, 32, 40]))
+    B = int(rng.integers(1, 4))
+    sh = S.Shape3D(ncam, K, bbox, G * spacing, spacing)
+    cam, intr, dist = S.make_rig(ncam, 50 + seed)
+    sets = [S.make_frameset(sh, cam, intr, dist, 10 * seed + b) for b in range(B)]
+    shift = rng.integers(-bbox // 3, bbox // 3 + 1, (B, ncam, 2)).astype(np.int32) if seed % 2 else np.zeros((B, ncam, 2), np.int32)
+    chm = np.stack([s[2] for s in sets]) + shift
+    L = ReprojectionLayer(cfg_of(sh), precision="bf16")
+    rep = lambda a: dev(a)[None].expand(B, *a.shape).contiguous()
+    vol, _ = L.forward_batched(torch.stack([dev(s[0]) for s in sets]), torch.stack([dev(s[1]) for s in sets]), dev(chm),
+                               rep(cam), rep(intr), rep(dist), post_divide=255.0, want_index=False)
+    for b in range(B):
+        want, _ = oracle.repro_layer_forward(oracle.pad_heatmaps(sets[b][0]), sets[b][1], chm[b], cam, intr, dist, sh.G, sh.spacing)
+        np.testing.assert_allclose(vol[b].cpu().numpy(), want / 255.0, rtol=2e-2, atol=2e-2 * 4 / 255, err_msg=str((seed, b, sh)))
+
+
 def test_batched_equals_single(oracle):
     """B frame sets in one launch == B reference-style B=1 forwards."""
     from jarvis_hybridnet_b200 import ReprojectionLayer
