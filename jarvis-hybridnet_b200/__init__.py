@@ -9,6 +9,7 @@ def __getattr__(name):
     import importlib
     table = {"ReprojectionLayer": "repro_layer", "V2VNet": "v2vnet", "HybridNet3D": "model", "accelerate": "model",
              "centroid_tail": "model", "shard_range": "model", "gather_results": "model",
+             "write_data3D_csv": "output", "create_info_file": "output",
              "locate_center": "predictor", "crop_normalize": "predictor", "accelerate_predictor": "predictor"}
     if name in table:
         return getattr(importlib.import_module("." + table[name], __name__), name)
