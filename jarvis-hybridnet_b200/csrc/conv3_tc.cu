@@ -273,7 +273,9 @@ tc_conv3_kernel(const C3Launch L)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty + ab));                 // accumulator buffer free again
-            asm volatile("bar.sync 1, %0;" ::"n"(128 * EW) : "memory");         // quadrant-boundary rows are in xch
+            // quadrant-boundary rows are in xch: only the four warps of one channel slice exchange rows, so each
+            // slice synchronises on its own named barrier (128 threads) instead of all 128 * EW epilogue threads
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + part) : "memory");
             if (lane == 0 && q > 0) {
 #pragma unroll
                 for (int i = 0; i < CW; ++i) o[i] += xw[((q - 1) * 2 + 0) * NOUT + c_base + i];
