@@ -76,7 +76,7 @@ int main()
     cudaMalloc(&d_out, 8);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int iters = 4096;
-    const int Ns[] = {16, 32, 48, 64, 96, 128, 192, 256};
+    const int Ns[] = {16, 32, 48, 64, 80, 96, 112, 128, 144, 160, 176, 192, 256};
     printf("grid mode lboA N cycles_per_mma ideal(=N/2)\n");
     for (int grid : {1, 148})
         for (int mode : {0, 1, 2, 3})
