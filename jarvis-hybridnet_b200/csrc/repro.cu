@@ -135,44 +135,6 @@ template <> __device__ __forceinline__ float to_store<float>(float v) { return v
 template <> __device__ __forceinline__ __nv_bfloat16 to_store<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ __half to_store<__half>(float v) { return __float2half_rn(v * HALF_STAGE_SCALE); }
 
-template <typename T> struct Vec;
-template <> struct Vec<float> {
-    static constexpr int N = KP / 4;                    // 6 x float4
-    static __device__ __forceinline__ void add(const float *p, float *acc)
-    {
-        const float4 *q = reinterpret_cast<const float4 *>(p);
-        float4 v[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = __ldg(q + i);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            acc[4 * i + 0] = __fadd_rn(acc[4 * i + 0], v[i].x);
-            acc[4 * i + 1] = __fadd_rn(acc[4 * i + 1], v[i].y);
-            acc[4 * i + 2] = __fadd_rn(acc[4 * i + 2], v[i].z);
-            acc[4 * i + 3] = __fadd_rn(acc[4 * i + 3], v[i].w);
-        }
-    }
-};
-template <> struct Vec<__nv_bfloat16> {
-    static constexpr int N = KP / 8;                    // 3 x 16 B
-    static __device__ __forceinline__ void add(const __nv_bfloat16 *p, float *acc)
-    {
-        const uint4 *q = reinterpret_cast<const uint4 *>(p);
-        uint4 v[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = __ldg(q + i);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {               // bf16 -> fp32 is a 16-bit shift
-                acc[8 * i + 2 * j + 0] += __uint_as_float(w[j] << 16);
-                acc[8 * i + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-            }
-        }
-    }
-};
-
 // 8 consecutive channels of one (camera, pixel) KP-vector, added into fp32 accumulators
 __device__ __forceinline__ void add8(const float *p, float *acc)
 {
