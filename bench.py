@@ -97,7 +97,7 @@ def make_inputs(sh, batch, n_batches, seed=0, distinct=8):
     for nb in range(n_batches):
         ids = [(nb * batch + i) % distinct for i in range(batch)]
         hm = np.stack([sets[i][0] for i in ids])
-        c3 = np.stack([sets[i][1] for i in ids])
+        c3 = np.stack([sets[i][1] for i in ids]).astype(np.float32)      # the C ABI takes fp32 centres (int centres are promoted exactly)
         chm = np.stack([sets[i][2] for i in ids])
         rep = lambda a: np.broadcast_to(a[None], (batch,) + a.shape).copy()
         batches.append((hm, c3, chm, rep(cam), rep(intr), rep(dist)))
@@ -323,6 +323,7 @@ def main():
     ap.add_argument("--job-frame-sets", type=int, default=0,
                     help="also run one sharded job of this many frame sets with a single gather at the end (BASELINE configs[3]: 100000)")
     ap.add_argument("--no-latency", action="store_true", help="skip the B=1 eager / CUDA-graph latency measurement")
+    ap.add_argument("--sub-batch", type=int, default=0, help="frame sets per internal pass of jhn_hybrid3d_forward (0 = library default)")
     args = ap.parse_args()
     claim_stdout()
     wl = dict(WORKLOADS[args.workload])
@@ -351,6 +352,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sh, B = wl["shape"], wl["batch"]
     K_steps, W = args.steps, max(args.warmup, 0)
+    sub_batch = _lib.set_sub_batch(args.sub_batch)
 
     precision = args.precision
     weights = S.make_v2v_weights(sh.K, 0, "he")
@@ -531,7 +533,8 @@ def main():
                     ms_per_step=ms / K_steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16" if precision == "bf16" else "f32", data="synthetic",
                     config=dict(workload=args.workload, ncam=sh.ncam, K=sh.K, heatmap=sh.hm, grid=sh.G,
-                                frame_sets_per_step_per_gpu=B, weights="random-init he (seed 0)",
+                                frame_sets_per_step_per_gpu=B, frame_sets_per_internal_pass=min(sub_batch, B),
+                                weights="random-init he (seed 0)",
                                 l2="inputs rotate through %d batches of %.0f MB (>> 126 MB L2)" % (n_pool, B * sh.ncam * sh.K * sh.hm ** 2 * 4 / 1e6),
                                 timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded",
                                 roi_share_of_heatmap=roi),

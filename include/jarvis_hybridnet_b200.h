@@ -49,6 +49,20 @@ enum jhn_lerp_mode {           /* rounding of ATen's trilinear lerp (SURVEY.md Â
     JHN_LERP_NO_FMA = 2        /* w0*a + w1*b, both products rounded                           */
 };
 
+/* Storage of the 2D key-point heat maps handed to the reprojection stage (SURVEY.md section 8b(1) "layout/dtype enum").
+ * The reference's effTrack head emits JHN_HM_F32_PLANAR (jarvis/efficienttrack/model.py:127,130 -> model.py:57-66);
+ * the channels-last 16-bit forms are the gather's native staging layout: one (camera, pixel) is ONE contiguous
+ * JHN_HM_CL_PITCH-channel vector, the 1-pixel zero border of F.pad (model.py:65-66) is materialised, channels
+ * K .. JHN_HM_CL_PITCH-1 are zero.  A producer that writes JHN_HM_F16_CL directly (jhn_heatmap_convert, or
+ * jhn_efftrack_head for the effTrack deconvolution) spares the staging pass and half of the input bytes. */
+enum jhn_heatmap_format {
+    JHN_HM_F32_PLANAR = 0,     /* fp32 [B][ncam][K][S][S], S = hs (padded) or hs-2 (un-padded)               */
+    JHN_HM_F16_CL = 1,         /* fp16 [B][ncam][hs][hs][24], values scaled by JHN_HM_F16_SCALE (exact 2^-4) */
+    JHN_HM_BF16_CL = 2         /* bf16 [B][ncam][hs][hs][24], unscaled                                       */
+};
+#define JHN_HM_CL_PITCH 24
+#define JHN_HM_F16_SCALE 0.0625f
+
 /* Layout of the feature volume handed from the reprojection stage to V2VNet. */
 enum jhn_volume_layout {
     JHN_VOL_NCDHW_F32 = 0,     /* [B][K][G][G][G] fp32 â€” the reference tensor (repro_layer.py:119) */
@@ -72,15 +86,22 @@ unsigned long long jhn_launch_count(void);
 void jhn_profile_enable(int on);
 int jhn_profile_collect(char *buf, int cap);
 int jhn_debug_set_gather_box_bytes(int bytes);
+/* Frame sets per internal pass of jhn_hybrid3d_forward (0 = library default, which keeps the activations of one pass
+ * inside the 126 MB L2).  Results do not depend on it.  Returns the value in effect. */
+int jhn_set_sub_batch(int frame_sets);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 â€” replaces F.pad (jarvis/hybridnet/model.py:65-66) + ReprojectionLayer.forward
  * (jarvis/hybridnet/repro_layer.py:110-119, :88-107, :40-85) + the /255 of model.py:72.
  *
- *   heatmaps        device fp32 [B][ncam][K][S][S]; S = hs if heatmaps_padded else hs-2.
- *                   (heatmaps_padded=1 is the tensor the reference passes to reproLayer.)
+ *   heatmaps        device, storage `hm_format` (enum jhn_heatmap_format).  JHN_HM_F32_PLANAR: fp32 [B][ncam][K][S][S],
+ *                   S = hs if heatmaps_padded else hs-2 (heatmaps_padded=1 is the tensor the reference passes to
+ *                   reproLayer).  The channels-last forms are always padded and need precision JHN_BF16.
  *   cameraMatrices  device fp32 [B][ncam][4][3]      intrinsicMatrices device fp32 [B][ncam][3][3]
- *   distortion      device fp32 [B][ncam][1][5]      center3D device i32 [B][3]
+ *   distortion      device fp32 [B][ncam][1][5]
+ *   center3D        device fp32 [B][3] (mm): added to the grid in fp32 exactly as `self.grid + center[0]`
+ *                   (repro_layer.py:113); the predictor passes integers (jarvis3D.py:183), the validation path
+ *                   multiples of GRID_SPACING (hybridnet.py:284-304) â€” both are taken as they are
  *   centerHM        device i32 [B][ncam][2]
  *   hs              padded heat-map side = BOUNDING_BOX_SIZE/2 + 2 (repro_layer.py:37)
  *   G, spacing      grid side ROI_CUBE_SIZE/GRID_SPACING (even) and GRID_SPACING in mm
@@ -90,14 +111,20 @@ int jhn_debug_set_gather_box_bytes(int bytes);
  *                   int64 `res` of repro_layer.py:82-83 (bit-exact parity target); may be NULL
  * ------------------------------------------------------------------------------------------------ */
 int jhn_reproject_workspace_bytes(int B, int ncam, int K, int hs, int G, int precision, size_t *bytes);
-int jhn_reproject_gather(const float *heatmaps, int heatmaps_padded,
+int jhn_reproject_gather(const void *heatmaps, int hm_format, int heatmaps_padded,
                          const float *cameraMatrices, const float *intrinsicMatrices,
                          const float *distortionCoefficients,
-                         const int32_t *center3D, const int32_t *centerHM,
+                         const float *center3D, const int32_t *centerHM,
                          int B, int ncam, int K, int hs, int G, float spacing,
                          int lerp_mode, float post_divide, int precision, int layout,
                          void *volume_out, int32_t *index_out,
                          void *workspace, size_t workspace_bytes, jhn_stream_t stream);
+
+/* Producer side of the channels-last formats: fp32 planar heat maps
+ * [B][ncam][K][S][S] -> `dst_format` (JHN_HM_F16_CL or JHN_HM_BF16_CL) [B][ncam][hs][hs][24] with the F.pad border.
+ * One HBM-bound pass; jhn_reproject_gather does the same internally when it is handed JHN_HM_F32_PLANAR. */
+int jhn_heatmap_convert(const float *heatmaps, int heatmaps_padded, int B, int ncam, int K, int hs,
+                        int dst_format, void *dst, jhn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 2 â€” replaces V2VNet (jarvis/hybridnet/v2vnet.py:86-102) in eval mode.
@@ -128,27 +155,33 @@ int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, in
 int jhn_v2v_debug_layer_workspace_bytes(const jhn_v2v *net, int layer, int B, int D, size_t *bytes);
 int jhn_v2v_debug_layer(const jhn_v2v *net, int layer, const float *in, int B, int D, float *out,
                         void *workspace, size_t workspace_bytes, jhn_stream_t stream);
+/* Test aid (bf16 networks only): the fused output layer + centroid tail (stage 3 inside the last GEMM's epilogue) on
+ * given activations.  `in` device fp32 NCDHW [B][2K][h][h][h] (rounded to bf16 on entry); outputs as jhn_centroid_reduce.
+ * Workspace: jhn_v2v_debug_layer_workspace_bytes(net, 11, B, h). */
+int jhn_v2v_debug_head_centroid(const jhn_v2v *net, const float *in, int B, int h, float spacing, float roi,
+                                const float *center3D, float *points, float *conf, int32_t *argmax,
+                                void *workspace, size_t workspace_bytes, jhn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 3 â€” replaces the inline tail of HybridNetBackbone.forward (jarvis/hybridnet/model.py:73-87):
  * softplus, sum-normalised centroid, confidence, voxel -> mm.
  *
- *   v2v_out   device fp32 [B][K][h][h][h]        center3D device i32 [B][3]
+ *   v2v_out   device fp32 [B][K][h][h][h]        center3D device fp32 [B][3]
  *   points    device fp32 [B][K][3] (mm)         conf device fp32 [B][K]
  *   argmax    optional device i32 [B][K]: first flat index of the per-key-point maximum
  * ------------------------------------------------------------------------------------------------ */
 int jhn_centroid_reduce(const float *v2v_out, int B, int K, int h, float spacing, float roi,
-                        const int32_t *center3D, float *points, float *conf, int32_t *argmax,
+                        const float *center3D, float *points, float *conf, int32_t *argmax,
                         jhn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stages 1-3 fused behind one call (model.py:65-88): heat maps in, key points out.
  * ------------------------------------------------------------------------------------------------ */
 int jhn_hybrid3d_workspace_bytes(const jhn_v2v *net, int B, int ncam, int hs, int G, size_t *bytes);
-int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps_padded,
+int jhn_hybrid3d_forward(const jhn_v2v *net, const void *heatmaps, int hm_format, int heatmaps_padded,
                          const float *cameraMatrices, const float *intrinsicMatrices,
                          const float *distortionCoefficients,
-                         const int32_t *center3D, const int32_t *centerHM,
+                         const float *center3D, const int32_t *centerHM,
                          int B, int ncam, int hs, int G, float spacing, float roi, int lerp_mode,
                          float *points, float *conf, int32_t *argmax,
                          void *workspace, size_t workspace_bytes, jhn_stream_t stream);

@@ -11,6 +11,9 @@ from . import build as _build
 FP32, BF16 = 0, 1
 VOL_NCDHW_F32, VOL_V2V_BF16 = 0, 1
 LERP_FMA_FIRST, LERP_FMA_SECOND, LERP_NO_FMA = 0, 1, 2
+HM_F32_PLANAR, HM_F16_CL, HM_BF16_CL = 0, 1, 2           # enum jhn_heatmap_format
+HM_CL_PITCH, HM_F16_SCALE = 24, 0.0625
+ABI_VERSION = _build.ABI_VERSION
 
 # every symbol include/jarvis_hybridnet_b200.h declares: name -> (restype, argtypes)
 _P = c_void_p
@@ -19,8 +22,11 @@ SYMBOLS = {
     "jhn_abi_version": (c_int, []),
     "jhn_check_device": (c_int, [c_int]),
     "jhn_reproject_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
-    "jhn_reproject_gather": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
+    "jhn_reproject_gather": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float,
                                      c_int, c_float, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "jhn_heatmap_convert": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "jhn_v2v_debug_head_centroid": (c_int, [_P, _P, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "jhn_set_sub_batch": (c_int, [c_int]),
     "jhn_v2v_create": (c_int, [POINTER(_P), c_int, c_int, c_int, _P, POINTER(_P)]),
     "jhn_v2v_destroy": (None, [_P]),
     "jhn_v2v_set_workspace_persistent": (c_int, [_P, c_int]),
@@ -30,7 +36,7 @@ SYMBOLS = {
     "jhn_v2v_debug_layer": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P, c_size_t, _P]),
     "jhn_centroid_reduce": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _P]),
     "jhn_hybrid3d_workspace_bytes": (c_int, [_P, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
-    "jhn_hybrid3d_forward": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float,
+    "jhn_hybrid3d_forward": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float,
                                      c_int, _P, _P, _P, _P, c_size_t, _P]),
     "jhn_center_locate": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -54,13 +60,18 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB):
-        try:
-            _build.build()
-        except Exception as e:  # no nvcc, compile error ...
+    try:
+        _build.build()                # no-op unless a source / header is newer than the library (a stale library would
+    except Exception as e:            # be called with the new argument lists)
+        if not os.path.exists(_build.LIB):
             raise RuntimeError(f"jarvis_hybridnet_b200: CUDA extension {_build.LIB} is missing and could not be "
                                f"built ({e}); there is no CPU fallback") from e
+        # no compiler on this box (the GPU box ships the prebuilt library): the ABI check below decides
     lib = ctypes.CDLL(_build.LIB)
+    lib.jhn_abi_version.restype = c_int
+    if lib.jhn_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"jarvis_hybridnet_b200: {_build.LIB} has ABI {lib.jhn_abi_version()}, the Python binding "
+                           f"expects {ABI_VERSION}; rebuild it (python jarvis-hybridnet_b200/build.py --force)")
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the library does not export it
         fn.restype = res
@@ -110,7 +121,38 @@ def stream_ptr():
 
 
 def require_cuda(*tensors):
+    """All tensors on ONE CUDA device; returns a context that makes it current (streams, handles and the library's
+    launches all follow the current device)."""
+    import torch
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("jarvis_hybridnet_b200 runs on CUDA tensors only (no CPU fallback); got a "
                                f"{t.device} tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"jarvis_hybridnet_b200: inputs live on different devices ({dev} and {t.device})")
+    return torch.cuda.device(dev) if dev is not None else None
+
+
+def set_sub_batch(n):
+    """Frame sets per internal pass of jhn_hybrid3d_forward (0 = default); returns the value in effect."""
+    return int(load().jhn_set_sub_batch(int(n)))
+
+
+def heatmap_convert(heatmaps, hs, fmt=HM_F16_CL):
+    """fp32 planar heat maps [B,ncam,K,S,S] (S = hs or hs-2) -> channels-last 16-bit [B,ncam,hs,hs,24] with the
+    F.pad border (`jhn_heatmap_convert`, the producer side of SURVEY.md section 8 row f2)."""
+    import torch
+    with require_cuda(heatmaps):
+        B, ncam, K, S, S2 = heatmaps.shape
+        if S != S2 or S not in (hs, hs - 2):
+            raise RuntimeError(f"heat maps are {S}x{S2}; expected {hs} (padded) or {hs - 2} per side")
+        hm = heatmaps.contiguous().float()
+        out = torch.empty((B, ncam, hs, hs, HM_CL_PITCH), dtype=torch.float16 if fmt == HM_F16_CL else torch.bfloat16,
+                          device=hm.device)
+        check(load().jhn_heatmap_convert(dptr(hm), int(S == hs), B, ncam, K, hs, int(fmt), dptr(out), stream_ptr()))
+    return out

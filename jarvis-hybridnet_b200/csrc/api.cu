@@ -61,7 +61,8 @@ int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st);
 void tc_destroy(jhn_v2v *net);
 size_t tc_workspace(const jhn_v2v *net, int B, int G);
 int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws,
-               size_t ws_bytes, cudaStream_t st, const TailArgs *tail);
+               size_t ws_bytes, cudaStream_t st, const TailArgs *tail, int carveB);
+int tc_debug_head(const jhn_v2v *net, const float *in, int B, int h, const TailArgs &tail, void *ws, size_t ws_bytes, cudaStream_t st);
 bool head_supported(int K, int cin_pad, int cout_pad, int D);
 
 int tc_debug_layer(const jhn_v2v *net, int l, const float *in, int B, int D, float *out, void *ws, size_t ws_bytes, cudaStream_t st);
@@ -82,11 +83,23 @@ using namespace jhn;
 extern "C" {
 
 const char *jhn_last_error(void) { return g_err; }
-int jhn_abi_version(void) { return 3; }
+int jhn_abi_version(void) { return 4; }
 unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 int jhn_debug_set_gather_box_bytes(int bytes) { return gather_set_box_bytes(bytes); }
+
+// Frame sets per internal pass of jhn_hybrid3d_forward.  Default 8: at the Example shape one pass then keeps a
+// convolution's input + output (2 x 42 MB) inside the 126 MB L2, so the normalisation passes and the next layer's
+// operand stream hit L2 instead of HBM (measured: profiles/r02_*subbatch*).  Frame sets are independent, so the
+// result does not depend on the value.
+static std::atomic<int> g_sub_batch{8};
+int jhn_set_sub_batch(int n)
+{
+    if (n <= 0) n = 8;
+    g_sub_batch.store(n, std::memory_order_relaxed);
+    return n;
+}
 
 // Synchronises the device, then writes one line per kernel name: "<name>\t<launches>\t<total_ms>\n".
 // Returns the number of bytes written (truncated to `cap`), and clears the records.
@@ -124,9 +137,9 @@ int jhn_reproject_workspace_bytes(int B, int ncam, int K, int hs, int G, int pre
     return JHN_OK;
 }
 
-int jhn_reproject_gather(const float *heatmaps, int heatmaps_padded, const float *cameraMatrices,
+int jhn_reproject_gather(const void *heatmaps, int hm_format, int heatmaps_padded, const float *cameraMatrices,
                          const float *intrinsicMatrices, const float *distortionCoefficients,
-                         const int32_t *center3D, const int32_t *centerHM, int B, int ncam, int K, int hs, int G,
+                         const float *center3D, const int32_t *centerHM, int B, int ncam, int K, int hs, int G,
                          float spacing, int lerp_mode, float post_divide, int precision, int layout,
                          void *volume_out, int32_t *index_out, void *workspace, size_t workspace_bytes,
                          jhn_stream_t stream)
@@ -136,14 +149,24 @@ int jhn_reproject_gather(const float *heatmaps, int heatmaps_padded, const float
         return fail(JHN_ERR_ARG, "jhn_reproject_gather: null pointer argument");
     JHN_TRY(check_repro_shape(B, ncam, K, hs, G));
     if (lerp_mode < 0 || lerp_mode > 2) return fail(JHN_ERR_ARG, "lerp_mode %d not in {0,1,2}", lerp_mode);
+    if (hm_format < JHN_HM_F32_PLANAR || hm_format > JHN_HM_BF16_CL) return fail(JHN_ERR_ARG, "hm_format %d unknown", hm_format);
     if (precision != JHN_FP32 && precision != JHN_BF16) return fail(JHN_ERR_ARG, "precision %d unknown", precision);
     if (layout != JHN_VOL_NCDHW_F32 && layout != JHN_VOL_V2V_BF16) return fail(JHN_ERR_ARG, "layout %d unknown", layout);
     if (!(post_divide > 0.f)) return fail(JHN_ERR_ARG, "post_divide must be > 0");
     if (((uintptr_t)workspace & 255) != 0) return fail(JHN_ERR_WORKSPACE, "workspace must be 256-byte aligned");
-    ReprojectArgs a{heatmaps, heatmaps_padded ? 1 : 0, cameraMatrices, intrinsicMatrices, distortionCoefficients,
+    ReprojectArgs a{heatmaps, hm_format, heatmaps_padded ? 1 : 0, cameraMatrices, intrinsicMatrices, distortionCoefficients,
                     center3D, centerHM, B, ncam, K, hs, G, spacing, lerp_mode, post_divide, precision, layout,
                     volume_out, index_out, 0};
     return reproject_launch(a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int jhn_heatmap_convert(const float *heatmaps, int heatmaps_padded, int B, int ncam, int K, int hs, int dst_format,
+                        void *dst, jhn_stream_t stream)
+{
+    if (!heatmaps || !dst) return fail(JHN_ERR_ARG, "jhn_heatmap_convert: null pointer argument");
+    if (B < 1 || ncam < 1 || K < 1 || K > KP || hs < 4 || hs > 1024)
+        return fail(JHN_ERR_SHAPE, "need B>=1, ncam>=1, 1<=K<=%d, 4<=hs<=1024 (got B=%d ncam=%d K=%d hs=%d)", KP, B, ncam, K, hs);
+    return heatmap_convert_launch(heatmaps, heatmaps_padded ? 1 : 0, B, ncam, K, hs, dst_format, dst, (cudaStream_t)stream);
 }
 
 int jhn_v2v_create(const float *const *tensors, int num_tensors, int K, int precision, jhn_stream_t stream,
@@ -161,8 +184,7 @@ int jhn_v2v_create(const float *const *tensors, int num_tensors, int K, int prec
     jhn_v2v *net = new (std::nothrow) jhn_v2v();
     if (!net) return fail(JHN_ERR_CUDA, "out of host memory");
     net->K = K; net->precision = precision; net->device = dev; net->blob = nullptr; net->tc = nullptr;
-    net->ws_persistent = 0; net->z_ws = nullptr; net->z_B = net->z_G = 0; net->z_kind = -1;
-    net->zv_ptr = nullptr; net->zv_B = net->zv_G = 0;
+    net->ws_persistent = 0; net->zc_n = 0;
     layer_table(K, net->desc);
     int s = v2v_f32_pack(net, tensors, (cudaStream_t)stream);
     if (s == JHN_OK && precision == JHN_BF16) s = tc_create(net, tensors, (cudaStream_t)stream);
@@ -174,8 +196,8 @@ int jhn_v2v_create(const float *const *tensors, int num_tensors, int K, int prec
 int jhn_v2v_set_workspace_persistent(jhn_v2v *net, int on)
 {
     if (!net) return fail(JHN_ERR_ARG, "net is null");
-    net->ws_persistent = on ? 1 : 0;
-    net->z_ws = nullptr; net->zv_ptr = nullptr;
+    { std::lock_guard<std::mutex> g(net->mu); net->ws_persistent = on ? 1 : 0; }
+    net->borders_forget();
     return JHN_OK;
 }
 
@@ -213,7 +235,7 @@ int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, in
         if (in_layout != JHN_VOL_NCDHW_F32) return fail(JHN_ERR_ARG, "fp32 V2V takes the NCDHW fp32 volume");
         return v2v_f32_forward(net, (const float *)volume_in, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream);
     }
-    return tc_forward(net, volume_in, in_layout, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
+    return tc_forward(net, volume_in, in_layout, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0);
 }
 
 int jhn_v2v_debug_layer_workspace_bytes(const jhn_v2v *net, int layer, int B, int D, size_t *bytes)
@@ -232,7 +254,18 @@ int jhn_v2v_debug_layer(const jhn_v2v *net, int layer, const float *in, int B, i
     return tc_debug_layer(net, layer, in, B, D, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int jhn_centroid_reduce(const float *v2v_out, int B, int K, int h, float spacing, float roi, const int32_t *center3D,
+int jhn_v2v_debug_head_centroid(const jhn_v2v *net, const float *in, int B, int h, float spacing, float roi,
+                                const float *center3D, float *points, float *conf, int32_t *argmax, void *workspace,
+                                size_t workspace_bytes, jhn_stream_t stream)
+{
+    if (!net || !net->tc || !in || !center3D || !points || !conf || !workspace)
+        return fail(JHN_ERR_ARG, "jhn_v2v_debug_head_centroid: null pointer argument / not a JHN_BF16 network");
+    if (B < 1 || h < 2 || h > 61) return fail(JHN_ERR_SHAPE, "bad B/h");
+    TailArgs tail{spacing, roi, center3D, points, conf, argmax, nullptr};
+    return tc_debug_head(net, in, B, h, tail, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int jhn_centroid_reduce(const float *v2v_out, int B, int K, int h, float spacing, float roi, const float *center3D,
                         float *points, float *conf, int32_t *argmax, jhn_stream_t stream)
 {
     if (!v2v_out || !center3D || !points || !conf) return fail(JHN_ERR_ARG, "jhn_centroid_reduce: null pointer argument");
@@ -243,23 +276,31 @@ int jhn_centroid_reduce(const float *v2v_out, int B, int K, int h, float spacing
 static int hybrid_layout(const jhn_v2v *net) { return net->precision == JHN_BF16 ? JHN_VOL_V2V_BF16 : JHN_VOL_NCDHW_F32; }
 static size_t hybrid_volume_bytes(const jhn_v2v *net, int B, int G);
 
+static int sub_batch_of(int B)
+{
+    const int n = g_sub_batch.load(std::memory_order_relaxed);
+    return B < n ? B : n;
+}
+
 int jhn_hybrid3d_workspace_bytes(const jhn_v2v *net, int B, int ncam, int hs, int G, size_t *bytes)
 {
     if (!bytes) return fail(JHN_ERR_ARG, "bytes is null");
     JHN_TRY(check_v2v_shape(net, B, G));
     JHN_TRY(check_repro_shape(B, ncam, net->K, hs, G));
+    const int SB = sub_batch_of(B);                     // the batch is walked in passes of SB frame sets over ONE workspace
     size_t v2v = 0;
-    JHN_TRY(jhn_v2v_workspace_bytes(net, B, G, &v2v));
+    JHN_TRY(jhn_v2v_workspace_bytes(net, SB, G, &v2v));
     const int h = G / 2;
-    *bytes = align_up(reproject_workspace(B, ncam, net->K, hs, G, net->precision), 256) +
-             align_up(hybrid_volume_bytes(net, B, G), 256) + align_up(v2v, 256) +
-             align_up((size_t)B * net->K * h * h * h * sizeof(float), 256);
+    size_t tail = (size_t)SB * net->K * h * h * h * sizeof(float);            // fp32 V2V output, or the fused head's accumulators
+    if (head_acc_bytes(SB, net->K) > tail) tail = head_acc_bytes(SB, net->K);
+    *bytes = align_up(reproject_workspace(SB, ncam, net->K, hs, G, net->precision), 256) +
+             align_up(hybrid_volume_bytes(net, SB, G), 256) + align_up(v2v, 256) + align_up(tail, 256);
     return JHN_OK;
 }
 
-int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps_padded, const float *cameraMatrices,
+int jhn_hybrid3d_forward(const jhn_v2v *net, const void *heatmaps, int hm_format, int heatmaps_padded, const float *cameraMatrices,
                          const float *intrinsicMatrices, const float *distortionCoefficients,
-                         const int32_t *center3D, const int32_t *centerHM, int B, int ncam, int hs, int G,
+                         const float *center3D, const int32_t *centerHM, int B, int ncam, int hs, int G,
                          float spacing, float roi, int lerp_mode, float *points, float *conf, int32_t *argmax,
                          void *workspace, size_t workspace_bytes, jhn_stream_t stream)
 {
@@ -267,35 +308,47 @@ int jhn_hybrid3d_forward(const jhn_v2v *net, const float *heatmaps, int heatmaps
     JHN_TRY(jhn_hybrid3d_workspace_bytes(net, B, ncam, hs, G, &need));
     if (!workspace || workspace_bytes < need) return fail(JHN_ERR_WORKSPACE, "hybrid3d workspace: need %zu bytes, got %zu", need, workspace_bytes);
     if (((uintptr_t)workspace & 255) != 0) return fail(JHN_ERR_WORKSPACE, "workspace must be 256-byte aligned");
-    const int h = G / 2;
-    char *p = (char *)workspace;
-    const size_t rws = align_up(reproject_workspace(B, ncam, net->K, hs, G, net->precision), 256);
-    void *ws_r = p; p += rws;
-    void *vol = p; p += align_up(hybrid_volume_bytes(net, B, G), 256);
-    size_t v2v = 0;
-    JHN_TRY(jhn_v2v_workspace_bytes(net, B, G, &v2v));
-    void *ws_v = p; p += align_up(v2v, 256);
-    float *vout = (float *)p;
     if (!heatmaps || !cameraMatrices || !intrinsicMatrices || !distortionCoefficients || !center3D || !centerHM || !points || !conf)
         return fail(JHN_ERR_ARG, "jhn_hybrid3d_forward: null pointer argument");
     if (lerp_mode < 0 || lerp_mode > 2) return fail(JHN_ERR_ARG, "lerp_mode %d not in {0,1,2}", lerp_mode);
-    ReprojectArgs ra{heatmaps, heatmaps_padded ? 1 : 0, cameraMatrices, intrinsicMatrices, distortionCoefficients,
-                     center3D, centerHM, B, ncam, net->K, hs, G, spacing, lerp_mode, 255.f, net->precision, hybrid_layout(net),
-                     vol, nullptr, 0};
-    if (net->precision == JHN_BF16) {
-        ra.borders_valid = net->ws_persistent && net->zv_ptr == vol && net->zv_B == B && net->zv_G == G;
-        net->zv_ptr = vol; net->zv_B = B; net->zv_G = G;
+    if (hm_format < JHN_HM_F32_PLANAR || hm_format > JHN_HM_BF16_CL) return fail(JHN_ERR_ARG, "hm_format %d unknown", hm_format);
+    const int h = G / 2, K = net->K;
+    const int SB = sub_batch_of(B);
+    char *p = (char *)workspace;
+    const size_t rws = align_up(reproject_workspace(SB, ncam, K, hs, G, net->precision), 256);
+    void *ws_r = p; p += rws;
+    void *vol = p; p += align_up(hybrid_volume_bytes(net, SB, G), 256);
+    size_t v2v = 0;
+    JHN_TRY(jhn_v2v_workspace_bytes(net, SB, G, &v2v));
+    void *ws_v = p; p += align_up(v2v, 256);
+    float *vout = (float *)p;
+    const int S = heatmaps_padded ? hs : hs - 2;
+    const size_t hm_stride = hm_format == JHN_HM_F32_PLANAR ? (size_t)ncam * K * S * S * sizeof(float)
+                                                            : (size_t)ncam * hs * hs * KP * 2;       // bytes per frame set
+    const int c2 = (2 * K + 15) / 16 * 16, c1 = (K + 15) / 16 * 16;
+    const bool fused_head = net->precision == JHN_BF16 && head_supported(K, c2, c1, h);
+    for (int b0 = 0; b0 < B; b0 += SB) {
+        const int nb = B - b0 < SB ? B - b0 : SB;
+        const size_t bc = (size_t)b0 * ncam;
+        ReprojectArgs ra{(const char *)heatmaps + (size_t)b0 * hm_stride, hm_format, heatmaps_padded ? 1 : 0, cameraMatrices + bc * 12,
+                         intrinsicMatrices + bc * 9, distortionCoefficients + bc * 5, center3D + (size_t)b0 * 3, centerHM + bc * 2,
+                         nb, ncam, K, hs, G, spacing, lerp_mode, 255.f, net->precision, hybrid_layout(net), vol, nullptr, 0};
+        // per-sample offsets of the padded layouts do not depend on the batch size, and the first pass always has nb == SB:
+        // a shorter last pass finds the borders of its samples already zero
+        if (net->precision == JHN_BF16) ra.borders_valid = net->borders_cached(vol, SB, G, 16) ? 1 : 0;
+        JHN_TRY(reproject_launch(ra, ws_r, rws, (cudaStream_t)stream));
+        float *pts = points + (size_t)b0 * K * 3, *cf = conf + (size_t)b0 * K;
+        int32_t *am = argmax ? argmax + (size_t)b0 * K : nullptr;
+        if (fused_head) {
+            // bf16 path: the output layer's epilogue is the centroid tail; the [B,K,h^3] volume is never materialised
+            TailArgs tail{spacing, roi, center3D + (size_t)b0 * 3, pts, cf, am, vout};
+            JHN_TRY(tc_forward(net, vol, hybrid_layout(net), nb, G, nullptr, ws_v, align_up(v2v, 256), (cudaStream_t)stream, &tail, SB));
+            continue;
+        }
+        JHN_TRY(jhn_v2v_forward(net, vol, hybrid_layout(net), nb, G, vout, ws_v, align_up(v2v, 256), stream));
+        JHN_TRY(jhn_centroid_reduce(vout, nb, K, h, spacing, roi, center3D + (size_t)b0 * 3, pts, cf, am, stream));
     }
-    JHN_TRY(reproject_launch(ra, ws_r, rws, (cudaStream_t)stream));
-    const int c2 = (2 * net->K + 15) / 16 * 16, c1 = (net->K + 15) / 16 * 16;
-    if (net->precision == JHN_BF16 && head_supported(net->K, c2, c1, h) &&
-        head_acc_bytes(B, net->K) <= (size_t)B * net->K * h * h * h * sizeof(float)) {
-        // bf16 path: the output layer's epilogue is the centroid tail; the [B,K,h^3] volume is never materialised
-        TailArgs tail{spacing, roi, center3D, points, conf, argmax, vout};
-        return tc_forward(net, vol, hybrid_layout(net), B, G, nullptr, ws_v, align_up(v2v, 256), (cudaStream_t)stream, &tail);
-    }
-    JHN_TRY(jhn_v2v_forward(net, vol, hybrid_layout(net), B, G, vout, ws_v, align_up(v2v, 256), stream));
-    return jhn_centroid_reduce(vout, B, net->K, h, spacing, roi, center3D, points, conf, argmax, stream);
+    return JHN_OK;
 }
 
 int jhn_center_locate(const float *center_heatmaps, int B, int ncam, int Hc, int Wc, int img_w, int img_h,

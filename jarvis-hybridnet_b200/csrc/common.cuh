@@ -66,9 +66,9 @@ constexpr int KP = 24;   // channel pitch of the channels-last heat-map staging 
 
 // ---- stage launchers (each returns a jhn_status) -------------------------------------------------
 struct ReprojectArgs {
-    const float *heatmaps; int padded;
+    const void *heatmaps; int hm_format; int padded;
     const float *cam, *intr, *dist;
-    const int32_t *center3D, *centerHM;
+    const float *center3D; const int32_t *centerHM;
     int B, ncam, K, hs, G;
     float spacing; int lerp_mode; float post_divide;
     int precision, layout;
@@ -78,11 +78,12 @@ struct ReprojectArgs {
 size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision);
 int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStream_t st);
 int gather_set_box_bytes(int bytes);   // test hook (jhn_debug_set_gather_box_bytes)
+int heatmap_convert_launch(const float *hm, int padded, int B, int ncam, int K, int hs, int dst_format, void *dst, cudaStream_t st);
 
 // zero the never-written border of a blocked+padded (BP/PS) bf16 tensor of `chunks_total` chunk volumes (conv_tc.cu)
 int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st);
 
-int centroid_launch(const float *v, int B, int K, int h, float spacing, float roi, const int32_t *center3D,
+int centroid_launch(const float *v, int B, int K, int h, float spacing, float roi, const float *center3D,
                     float *points, float *conf, int32_t *argmax, cudaStream_t st);
 
 int center_locate_launch(const float *hm, int B, int ncam, int Hc, int Wc, int img_w, int img_h, int cdis, int bbox_hw,

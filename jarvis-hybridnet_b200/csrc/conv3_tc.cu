@@ -41,7 +41,7 @@ struct C3Launch {
     const __nv_bfloat16 *w;                            // [dz*3+dy][KC][dx*NOUT+co][8] bf16
     const float *bias;                                 // [NOUT]
     uint4 *out;                                        // BP bf16 output [B][KC][D+2][(D+2)^2]
-    float *stats;                                      // [B][NOUT][2] or null
+    StatPart stats;                                    // per-CTA partial sums of the following InstanceNorm (part may be null)
     int B, D, NT, total_tiles;
     int NS, PB;                                        // ring slots, positions per plane box
     int add_bias;                                      // 0 when an InstanceNorm follows (it cancels the bias exactly)
@@ -201,15 +201,14 @@ tc_conv3_kernel(const C3Launch L)
         for (int i = 0; i < CW; ++i) { s1[i] = 0.f; s2[i] = 0.f; bias_r[i] = L.add_bias ? bias_s[c_base + i] : 0.f; }
         int stat_b = -1;
         auto flush = [&](int b) {
+            const int slot = ((int)blockIdx.x + b) * 4 + q;
+            float2 *dst = reinterpret_cast<float2 *>(L.stats.part) + (size_t)slot * NOUT + c_base;
 #pragma unroll
             for (int i = 0; i < CW; ++i) {
                 float a = s1[i], c = s2[i];
 #pragma unroll
                 for (int s = 16; s > 0; s >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, s); c += __shfl_xor_sync(0xffffffffu, c, s); }
-                if (lane == 0) {
-                    atomicAdd(L.stats + ((size_t)b * NOUT + c_base + i) * 2, a);
-                    atomicAdd(L.stats + ((size_t)b * NOUT + c_base + i) * 2 + 1, c);
-                }
+                if (lane == 0) dst[i] = make_float2(a, c);
                 s1[i] = 0.f; s2[i] = 0.f;
             }
         };
@@ -223,7 +222,7 @@ tc_conv3_kernel(const C3Launch L)
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c_base;
         for (int t = t_begin; t < t_end; ++t) {
             if (column_changed) {
-                if (L.stats && b != stat_b) {
+                if (L.stats.part && b != stat_b) {
                     if (stat_b >= 0) flush(stat_b);
                     stat_b = b;
                 }
@@ -310,7 +309,7 @@ tc_conv3_kernel(const C3Launch L)
                 if (++pt == L.NT) { pt = 0; ++b; }
             }
         }
-        if (L.stats && stat_b >= 0) flush(stat_b);
+        if (L.stats.part && stat_b >= 0) flush(stat_b);
     }
     tc_fence_before();
     __syncthreads();
@@ -381,17 +380,19 @@ static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st
     return JHN_OK;
 }
 
-int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, float *stats, int B, int D,
+int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, StatPart *stats, int B, int D,
               int NS, int PB, int sms, int add_bias, cudaStream_t st)
 {
     C3Launch L;
-    L.in = (const uint4 *)in; L.w = w; L.bias = bias; L.out = (uint4 *)out; L.stats = stats; L.B = B; L.D = D;
+    L.in = (const uint4 *)in; L.w = w; L.bias = bias; L.out = (uint4 *)out; L.B = B; L.D = D;
     const int Wp = D + 2;
     L.NT = cdiv((long long)(D - 1) * Wp + D, C3_VALID);
     L.total_tiles = B * L.NT * D;
     L.NS = NS; L.PB = PB; L.add_bias = add_bias;
     const size_t smem = c3_weight_bytes(NOUT) + (size_t)NS * (NOUT / 8) * PB * 16 + c3_tail_bytes(NOUT);
     const int grid = L.total_tiles < sms ? L.total_tiles : sms;
+    if (stats) { stats->grid = grid; stats->Tb = L.NT * D; stats->T = L.total_tiles; L.stats = *stats; }
+    else L.stats = StatPart{nullptr, 0, 0, 0};
     switch (NOUT) {
     case 16: return c3_launch_t<16, 2>(L, grid, smem, st);
     case 32: return c3_launch_t<32, 2>(L, grid, smem, st);

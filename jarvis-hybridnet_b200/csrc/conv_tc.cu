@@ -62,7 +62,7 @@ struct TcLaunch {
     const __nv_bfloat16 *w;                           // [tap][KC][NOUT][8] bf16
     const float *bias;                                // [NOUT] fp32 (zero padded)
     void *out;                                        // BP bf16 (RAW/CONVT) or NCDHW fp32 (HEAD)
-    float *stats;                                     // [B][NOUT][2] (sum, sumsq) or null
+    StatPart stats;                                   // per-CTA partial (sum, sumsq) of the following InstanceNorm (part may be null)
     int B, D;                                         // samples, grid side of the GEMM-row positions
     int CJ_in;                                        // chunks per sample in the input tensor (TMA dim 3)
     int CJ_out;                                       // chunks per sample in the output tensor
@@ -273,16 +273,19 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
         const int col = lane & 15, which = lane >> 4;                // statistics ownership
         float acc_stat[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int stat_b = -1;
+        auto flush_stats = [&](int b) {               // this warp's slot of sample b: plain stores, summed in slot order by the consumer
+            const int slot = ((int)blockIdx.x + b) * 4 + wq;
+            float *dst = L.stats.part + (size_t)slot * P.NOUT * 2;
+#pragma unroll
+            for (int ci = 0; ci < 6; ++ci)
+                if (ci * 16 < P.NOUT && (ci & 1) == chalf) { dst[(ci * 16 + col) * 2 + which] = acc_stat[ci]; acc_stat[ci] = 0.f; }
+        };
         int ab = 0; uint32_t aphase = 0;
         const size_t plane16 = (size_t)PP;                           // 16-byte units per z-plane
         for (int t = t_begin; t < t_end; ++t) {
             const TileCoord c = decode_tile(t, L, P.tile_taps);
-            if (L.stats && c.b != stat_b) {
-                if (stat_b >= 0) {
-#pragma unroll
-                    for (int ci = 0; ci < 6; ++ci)
-                        if (ci * 16 < P.NOUT && (ci & 1) == chalf) { atomicAdd(L.stats + ((size_t)stat_b * P.NOUT + ci * 16 + col) * 2 + which, acc_stat[ci]); acc_stat[ci] = 0.f; }
-                }
+            if (L.stats.part && c.b != stat_b) {
+                if (stat_b >= 0) flush_stats(stat_b);
                 stat_b = c.b;
             }
             const int p = Wp + 1 + c.pt * TILE_M + m;
@@ -340,7 +343,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
                             o[base] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             o[base + (size_t)Wp2 * plane2] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                         }
-                        if (L.stats) {                                 // column sums through a padded smem tile
+                        if (L.stats.part) {                            // column sums through a padded smem tile
 #pragma unroll
                             for (int i = 0; i < 16; ++i) tile[lane * 17 + i] = v[i];
                             __syncwarp();
@@ -358,11 +361,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
             if (lane == 0) mbar_arrive(smem_u32(tempty + ab));
             if (++ab == 2) { ab = 0; aphase ^= 1; }
         }
-        if (L.stats && stat_b >= 0) {
-#pragma unroll
-            for (int ci = 0; ci < 6; ++ci)
-                if (ci * 16 < P.NOUT && (ci & 1) == chalf) atomicAdd(L.stats + ((size_t)stat_b * P.NOUT + ci * 16 + col) * 2 + which, acc_stat[ci]);
-        }
+        if (L.stats.part && stat_b >= 0) flush_stats(stat_b);
     }
     tc_fence_before();
     __syncthreads();
@@ -448,20 +447,34 @@ int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st
 constexpr int NORM_THREADS = 256, NORM_UNROLL = 3;
 template <bool HAS_RES, bool HAS_POST, bool HAS_PS>
 __global__ void __launch_bounds__(NORM_THREADS)
-tc_norm_act_kernel(uint4 *__restrict__ x, const float *__restrict__ stats, const uint4 *__restrict__ residual,
+tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__restrict__ residual,
                    const uint4 *__restrict__ post_add, uint4 *__restrict__ ps_out, int relu, int D, int CJ, int NOUT,
                    float inv_count, float eps, uint32_t wp_magic)
 {
     __shared__ float sc[16];                                          // mean[8], rstd[8]
+    __shared__ double red[32][8][2];
     const int z = blockIdx.x, bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
     const int Wp = D + 2, PP = Wp * Wp;
+    {
+        // second stage of the statistics: the producing kernel's per-CTA slots of sample b, added in slot order in fp64
+        // (strided over 32 thread groups, then a fixed-order sum over the groups): identical bits on every run
+        const int c0 = stat_owner((long long)b * stats.Tb, stats.grid, stats.T);
+        const int c1 = stat_owner((long long)(b + 1) * stats.Tb - 1, stats.grid, stats.T);
+        const int nslots = (c1 - c0 + 1) * 4;
+        const int ch = threadIdx.x & 7, grp = threadIdx.x >> 3;
+        const float2 *src = reinterpret_cast<const float2 *>(stats.part) + (size_t)(c0 + b) * 4 * NOUT + j * 8 + ch;
+        double s1 = 0.0, s2 = 0.0;
+        for (int s = grp; s < nslots; s += NORM_THREADS / 8) { const float2 v = src[(size_t)s * NOUT]; s1 += (double)v.x; s2 += (double)v.y; }
+        red[grp][ch][0] = s1; red[grp][ch][1] = s2;
+    }
+    __syncthreads();
     if (threadIdx.x < 8) {
-        const int c = j * 8 + threadIdx.x;
-        const float sum = stats[((size_t)b * NOUT + c) * 2], sq = stats[((size_t)b * NOUT + c) * 2 + 1];
-        const float mean = sum * inv_count;
-        const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
-        sc[threadIdx.x] = mean;
-        sc[8 + threadIdx.x] = rsqrtf(var + eps);
+        double s1 = 0.0, s2 = 0.0;
+        for (int g = 0; g < NORM_THREADS / 8; ++g) { s1 += red[g][threadIdx.x][0]; s2 += red[g][threadIdx.x][1]; }
+        const double mean = s1 * (double)inv_count;
+        const double var = fmax(s2 * (double)inv_count - mean * mean, 0.0);
+        sc[threadIdx.x] = (float)mean;
+        sc[8 + threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
     float mean[8], rstd[8];
@@ -592,7 +605,7 @@ static inline int tiles_per_plane(int D) { return cdiv((long long)(D - 1) * (D +
 size_t c3_weight_bytes(int NOUT);
 bool c3_plan(int NOUT, int D, int max_smem, int *NS, int *PB);
 int c3_pack(const float *src, __nv_bfloat16 *dst, int cout, int cin, int NOUT, cudaStream_t st);
-int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, float *stats, int B, int D,
+int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, StatPart *stats, int B, int D,
               int NS, int PB, int sms, int add_bias, cudaStream_t st);
 
 struct TcLayer {
@@ -762,7 +775,7 @@ struct TcBuffers {
     uint4 *A, *Bq, *C, *Dd, *E;    // h-grid BP tensors      [B][C2/8][h+2][(h+2)^2]
     uint4 *Xps;                    // PS copy of front1 out  [B][8][C2/8][q+2][(q+2)^2]
     uint4 *Pq, *Q, *R;             // q-grid BP tensors      [B][C4/8][q+2][(q+2)^2]
-    float *stats;                  // [11][B][96][2]
+    float *stats;                  // [11][stat_slots][96][2] per-CTA partial sums (tc_ptx.cuh)
 };
 
 static size_t bp_units(int B, int cpad, int D) { return (size_t)B * (cpad / 8) * (D + 2) * (D + 2) * (D + 2); }
@@ -777,7 +790,7 @@ static void carve(Arena &a, const jhn_v2v *net, int B, int G, TcBuffers &t, bool
     t.Dd = a.take<uint4>(bp_units(B, c2, h)); t.E = a.take<uint4>(bp_units(B, c2, h));
     t.Xps = a.take<uint4>(8 * bp_units(B, c2, q));
     t.Pq = a.take<uint4>(bp_units(B, c4, q)); t.Q = a.take<uint4>(bp_units(B, c4, q)); t.R = a.take<uint4>(bp_units(B, c4, q));
-    t.stats = a.take<float>((size_t)11 * B * 96 * 2);
+    t.stats = a.take<float>((size_t)11 * stat_slots(256, B) * 96 * 2);
 }
 
 size_t tc_volume_bytes(const jhn_v2v *net, int B, int G)
@@ -799,7 +812,7 @@ struct TcCtx {
     bool keep_bias;                                   // debug hook: raw conv output incl. bias; forward: an InstanceNorm follows
 
     // in: BP or PS tensor with `chunks_in` chunks per sample on grid side D (the GEMM-row grid)
-    int conv(int l, const uint4 *in, int chunks_in, int D, void *out, int chunks_out, float *stats) const
+    int conv(int l, const uint4 *in, int chunks_in, int D, void *out, int chunks_out, StatPart *stats) const
     {
         const TcLayer &T = net->tc->layer[l];
         int ns = 0, pb = 0;
@@ -810,16 +823,18 @@ struct TcCtx {
         JHN_TRY(build_program(P, kLayerKind[l], T.cin_pad, T.cout_pad, D, net->tc->max_smem));
         P.KC_load = (net->desc[l].cin + 7) / 8 < P.KC ? (net->desc[l].cin + 7) / 8 : P.KC;
         TcLaunch L;
-        L.in = in; L.w = T.w; L.bias = T.bias; L.out = out; L.stats = stats; L.B = B; L.D = D; L.CJ_in = chunks_in; L.CJ_out = chunks_out;
+        L.in = in; L.w = T.w; L.bias = T.bias; L.out = out; L.B = B; L.D = D; L.CJ_in = chunks_in; L.CJ_out = chunks_out;
         L.NT = tiles_per_plane(D); L.total_tiles = B * D * L.NT * P.tile_taps; L.Kout = T.cout;
         const int grid = L.total_tiles < sms ? L.total_tiles : sms;
+        if (stats) { stats->grid = grid; stats->Tb = D * L.NT * P.tile_taps; stats->T = L.total_tiles; L.stats = *stats; }
+        else L.stats = StatPart{nullptr, 0, 0, 0};
         const char *name = kLayerKind[l] == 0 ? (P.resident ? "tc_conv_k3_resident" : "tc_conv_k3_streamed")
                            : kLayerKind[l] == 1 ? "tc_conv_front_k3s2" : kLayerKind[l] == 2 ? "tc_conv_pool_k2s2"
                            : kLayerKind[l] == 3 ? "tc_conv_up_convT" : "tc_conv_head_1x1";
         JHN_LAUNCH(name, st, tc_conv_kernel<<<grid, TC_THREADS, program_smem(P), st>>>(P, L));
         return JHN_OK;
     }
-    int norm(uint4 *x, const float *stats, int l, int D, const uint4 *residual, bool relu, const uint4 *post_add, uint4 *ps) const
+    int norm(uint4 *x, const StatPart &stats, int l, int D, const uint4 *residual, bool relu, const uint4 *post_add, uint4 *ps) const
     {
         const TcLayer &T = net->tc->layer[l];
         const int nv = D * D * D, CJ = T.cout_pad / 8, Wp = D + 2;
@@ -844,20 +859,23 @@ struct TcCtx {
 
 bool head_supported(int K, int cin_pad, int cout_pad, int D);
 int head_centroid_launch(const void *in, const __nv_bfloat16 *w, const float *bias, int B, int D, int K, int cin_pad, int cout_pad,
-                         float spacing, float roi, const int32_t *center3D, float *points, float *conf, int32_t *argmax, void *acc,
+                         float spacing, float roi, const float *center3D, float *points, float *conf, int32_t *argmax, void *acc,
                          int sms, int max_smem, cudaStream_t st);
 
 // `tail` non-null: the output layer runs fused with the centroid tail and `out` is not written (may be null).
+// `carveB` >= B: the workspace is carved for carveB frame sets (a caller that walks a batch in sub-batches keeps one
+// carving, so the cached zero borders stay valid for a shorter last pass); 0 = B.
 int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws, size_t ws_bytes,
-               cudaStream_t st, const TailArgs *tail)
+               cudaStream_t st, const TailArgs *tail, int carveB)
 {
+    if (carveB < B) carveB = B;
     const TcNet *tc = net->tc;
     if (!tc) return fail(JHN_ERR_ARG, "network was not created with JHN_BF16");
     const int h = G / 2, q = G / 4;
     if (h + 2 > 63) return fail(JHN_ERR_SHAPE, "bf16 path supports grid sides up to 122; got %d", G);
     Arena a(ws, ws_bytes);
     TcBuffers t;
-    carve(a, net, B, G, t, in_layout != JHN_VOL_V2V_BF16);
+    carve(a, net, carveB, G, t, in_layout != JHN_VOL_V2V_BF16);
     if (!a.ok()) return fail(JHN_ERR_WORKSPACE, "v2v bf16 workspace: need %zu bytes, got %zu", a.off, ws_bytes);
     int dev = 0, sms = 0;
     JHN_CUDA(cudaGetDevice(&dev));
@@ -865,51 +883,53 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
     TcCtx c{net, B, st, sms, false};
     const int j1 = tc->layer[L_FRONT0].cin_pad / 8, j2 = tc->layer[L_FRONT0].cout_pad / 8, j4 = tc->layer[L_POOL].cout_pad / 8;
     const uint4 *vol = (const uint4 *)volume_in;
-    const bool borders_valid = net->ws_persistent && net->z_ws == ws && net->z_B == B && net->z_G == G && net->z_kind == in_layout;
+    const bool borders_valid = net->borders_cached(ws, carveB, G, in_layout);
     if (in_layout != JHN_VOL_V2V_BF16) {
-        if (!borders_valid) JHN_TRY(c.zero_border(t.vol_ps, B * 8 * j1, h));
+        if (!borders_valid) JHN_TRY(c.zero_border(t.vol_ps, carveB * 8 * j1, h));
         const size_t nv = (size_t)G * G * G;
         JHN_LAUNCH("tc_ncdhw_to_ps_kernel", st,
                    tc_ncdhw_to_ps_kernel<<<dim3(cdiv(nv, 256), B * j1), 256, 0, st>>>((const float *)volume_in, t.vol_ps, net->K, G, j1));
         vol = t.vol_ps;
     }
-    JHN_CUDA(cudaMemsetAsync(t.stats, 0, (size_t)11 * B * 96 * 2 * sizeof(float), st));
     if (!borders_valid) {
         ZeroJobs J;
         uint4 *ptrs[9] = {t.A, t.Bq, t.C, t.Dd, t.E, t.Pq, t.Q, t.R, t.Xps};
-        const int chunks[9] = {B * j2, B * j2, B * j2, B * j2, B * j2, B * j4, B * j4, B * j4, B * 8 * j2};
+        const int CB = carveB;
+        const int chunks[9] = {CB * j2, CB * j2, CB * j2, CB * j2, CB * j2, CB * j4, CB * j4, CB * j4, CB * 8 * j2};
         const int sides[9] = {h, h, h, h, h, q, q, q, q};
         J.n = 9;
         int total = 0;
         for (int i = 0; i < 9; ++i) { J.first[i] = total; J.D[i] = sides[i]; J.p[i] = ptrs[i]; total += chunks[i] * (sides[i] + 2); }
         J.first[9] = total;
         JHN_LAUNCH("tc_zero_border_kernel", st, tc_zero_border_multi_kernel<<<total, 128, 0, st>>>(J));
-        net->z_ws = ws; net->z_B = B; net->z_G = G; net->z_kind = in_layout;
     }
-    auto S = [&](int i) { return t.stats + (size_t)i * B * 96 * 2; };
+    if (sms > 256) return fail(JHN_ERR_ARCH, "device has %d SMs; the statistics slots are sized for <= 256", sms);
+    StatPart sp[11];
+    for (int i = 0; i < 11; ++i) sp[i] = StatPart{t.stats + (size_t)i * stat_slots(256, carveB) * 96 * 2, 0, 0, 0};
+    auto S = [&](int i) { return &sp[i]; };
 
     JHN_TRY(c.conv(L_FRONT0, vol, 8 * j1, h, t.A, j2, S(0)));                         // front_layers.0   v2vnet.py:90
-    JHN_TRY(c.norm(t.A, S(0), L_FRONT0, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.norm(t.A, *S(0), L_FRONT0, h, nullptr, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_FRONT1A, t.A, j2, h, t.Bq, j2, S(1)));                           // front_layers.1 (Res3DBlock)
-    JHN_TRY(c.norm(t.Bq, S(1), L_FRONT1A, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.norm(t.Bq, *S(1), L_FRONT1A, h, nullptr, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_FRONT1B, t.Bq, j2, h, t.C, j2, S(2)));
-    JHN_TRY(c.norm(t.C, S(2), L_FRONT1B, h, t.A, true, nullptr, t.Xps));              // x = C (+ PS copy for the pool)
+    JHN_TRY(c.norm(t.C, *S(2), L_FRONT1B, h, t.A, true, nullptr, t.Xps));              // x = C (+ PS copy for the pool)
     JHN_TRY(c.conv(L_SKIPA, t.C, j2, h, t.A, j2, S(3)));                              // skip_res1        :76
-    JHN_TRY(c.norm(t.A, S(3), L_SKIPA, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.norm(t.A, *S(3), L_SKIPA, h, nullptr, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_SKIPB, t.A, j2, h, t.Bq, j2, S(4)));
-    JHN_TRY(c.norm(t.Bq, S(4), L_SKIPB, h, t.C, true, nullptr, nullptr));             // s = Bq
+    JHN_TRY(c.norm(t.Bq, *S(4), L_SKIPB, h, t.C, true, nullptr, nullptr));             // s = Bq
     JHN_TRY(c.conv(L_POOL, t.Xps, 8 * j2, q, t.Pq, j4, S(5)));                        // encoder_pool1    :77
-    JHN_TRY(c.norm(t.Pq, S(5), L_POOL, q, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.norm(t.Pq, *S(5), L_POOL, q, nullptr, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_MIDA, t.Pq, j4, q, t.Q, j4, S(6)));                              // mid_res          :78
-    JHN_TRY(c.norm(t.Q, S(6), L_MIDA, q, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.norm(t.Q, *S(6), L_MIDA, q, nullptr, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_MIDB, t.Q, j4, q, t.R, j4, S(7)));
-    JHN_TRY(c.norm(t.R, S(7), L_MIDB, q, t.Pq, true, nullptr, nullptr));
+    JHN_TRY(c.norm(t.R, *S(7), L_MIDB, q, t.Pq, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_UP, t.R, j4, q, t.A, j2, S(8)));                                 // decoder_upsample1 :79
-    JHN_TRY(c.norm(t.A, S(8), L_UP, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.norm(t.A, *S(8), L_UP, h, nullptr, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_DECA, t.A, j2, h, t.Dd, j2, S(9)));                              // decoder_res1     :80
-    JHN_TRY(c.norm(t.Dd, S(9), L_DECA, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.norm(t.Dd, *S(9), L_DECA, h, nullptr, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_DECB, t.Dd, j2, h, t.E, j2, S(10)));
-    JHN_TRY(c.norm(t.E, S(10), L_DECB, h, t.A, true, t.Bq, nullptr));                 // relu(.. + x) + skip   :81
+    JHN_TRY(c.norm(t.E, *S(10), L_DECB, h, t.A, true, t.Bq, nullptr));                 // relu(.. + x) + skip   :81
     if (tail) {                                                                        // output_layer + model.py:73-87
         const TcLayer &H = tc->layer[L_HEAD];
         return head_centroid_launch(t.E, H.w, H.bias, B, h, net->K, H.cin_pad, H.cout_pad, tail->spacing, tail->roi, tail->center3D,
@@ -936,13 +956,13 @@ int tc_debug_layer(const jhn_v2v *net, int l, const float *in, int B, int D, flo
     const bool ps = kind == 1 || kind == 2;
     uint4 *tin = a.take<uint4>(ps ? 8 * bp_units(B, T.cin_pad, D) : bp_units(B, T.cin_pad, D));
     uint4 *tout = a.take<uint4>(bp_units(B, T.cout_pad, Dout));
-    float *stats = a.take<float>((size_t)B * 96 * 2);
+    float *stats = a.take<float>((size_t)stat_slots(256, B) * 96 * 2);
     if (!a.ok()) return fail(JHN_ERR_WORKSPACE, "debug layer workspace: need %zu bytes, got %zu", a.off, ws_bytes);
     int dev = 0, sms = 0;
     JHN_CUDA(cudaGetDevice(&dev));
     JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     TcCtx c{net, B, st, sms, true};
-    JHN_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 96 * 2 * sizeof(float), st));
+    StatPart sp{stats, 0, 0, 0};
     JHN_TRY(c.zero_border(tin, B * (ps ? 8 : 1) * ji, D));
     if (ps) {
         const size_t nv = (size_t)Din * Din * Din;
@@ -953,10 +973,32 @@ int tc_debug_layer(const jhn_v2v *net, int l, const float *in, int B, int D, flo
     }
     if (kind == 4) return c.conv(l, tin, ji, D, out, 0, nullptr);
     JHN_TRY(c.zero_border(tout, B * jo, Dout));
-    JHN_TRY(c.conv(l, tin, (ps ? 8 : 1) * ji, D, tout, jo, stats));
+    JHN_TRY(c.conv(l, tin, (ps ? 8 : 1) * ji, D, tout, jo, &sp));
     const int nvo = Dout * Dout * Dout;
     JHN_LAUNCH("tc_bp_to_ncdhw_kernel", st, tc_bp_to_ncdhw_kernel<<<dim3(cdiv(nvo, 256), B * jo), 256, 0, st>>>(tout, out, d.cout, Dout, jo));
     return JHN_OK;
+}
+
+// Test hook: fp32 NCDHW activations -> BP bf16 -> fused output layer + centroid tail (head_tc.cu).
+int tc_debug_head(const jhn_v2v *net, const float *in, int B, int h, const TailArgs &tail, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    const TcNet *tc = net->tc;
+    const TcLayer &H = tc->layer[L_HEAD];
+    if (!head_supported(net->K, H.cin_pad, H.cout_pad, h)) return fail(JHN_ERR_SHAPE, "fused head does not support K=%d", net->K);
+    Arena a(ws, ws_bytes);
+    const int ji = H.cin_pad / 8;
+    uint4 *tin = a.take<uint4>(bp_units(B, H.cin_pad, h));
+    char *acc = a.take<char>(head_acc_bytes(B, net->K));
+    if (!a.ok()) return fail(JHN_ERR_WORKSPACE, "debug head workspace: need %zu bytes, got %zu", a.off, ws_bytes);
+    int dev = 0, sms = 0;
+    JHN_CUDA(cudaGetDevice(&dev));
+    JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    JHN_TRY(tc_zero_border_launch(tin, B * ji, h, st));
+    const int nv = h * h * h;
+    JHN_LAUNCH("tc_ncdhw_to_bp_kernel", st,
+               tc_ncdhw_to_bp_kernel<<<dim3(cdiv(nv, 256), B * ji), 256, 0, st>>>(in, tin, net->desc[L_HEAD].cin, h, ji));
+    return head_centroid_launch(tin, H.w, H.bias, B, h, net->K, H.cin_pad, H.cout_pad, tail.spacing, tail.roi, tail.center3D,
+                                tail.points, tail.conf, tail.argmax, acc, sms, tc->max_smem, st);
 }
 
 size_t tc_debug_workspace(const jhn_v2v *net, int l, int B, int D)
@@ -968,7 +1010,7 @@ size_t tc_debug_workspace(const jhn_v2v *net, int l, int B, int D)
     const bool ps = kind == 1 || kind == 2;
     a.take<uint4>(ps ? 8 * bp_units(B, T.cin_pad, D) : bp_units(B, T.cin_pad, D));
     a.take<uint4>(bp_units(B, T.cout_pad, Dout));
-    a.take<float>((size_t)B * 96 * 2);
+    a.take<float>((size_t)stat_slots(256, B) * 96 * 2);
     return a.off;
 }
 

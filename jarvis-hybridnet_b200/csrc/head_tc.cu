@@ -9,7 +9,9 @@
 //     warp 1      MMA issuer: KC/2 tcgen05.mma (M=128, N=NOUT, K=16) per tile, accumulators double-buffered in TMEM
 //     warps 2-9   epilogue, two per TMEM lane quadrant, each owning half of the key points: tcgen05.ld -> +bias ->
 //                 softplus -> per-thread running sums (n, sum hf*i, sum hf*j, sum hf*k), max hf, (max raw, argmax);
-//                 warp-reduced and pushed with atomics when the CTA's tile range leaves a frame set.
+//                 warp-reduced when the CTA's tile range leaves a frame set: the four sums go to the warp's own slot
+//                 (plain stores; the finalize kernel adds a frame set's slots in CTA order in fp64, so the key points
+//                 are bit-identical from run to run), the maxima are order-independent atomicMax.
 // The argmax is an atomicMax on a 64-bit key (order-preserving bits of the raw value, ~flat index), i.e. the first
 // flat index of the maximum, independent of scheduling.
 #include "tc_ptx.cuh"
@@ -23,7 +25,7 @@ struct HeadLaunch {
     const uint4 *in;                                   // BP bf16 input [B][KC][D+2][(D+2)^2]
     const __nv_bfloat16 *w;                            // [KC][NOUT][8] bf16
     const float *bias;                                 // [NOUT]
-    float *sums;                                       // [B][K][4]  n, sx, sy, sz
+    float *sums;                                       // [4 * (grid + B)][K][4]  per-CTA, per-quadrant partial n, sx, sy, sz (tc_ptx.cuh)
     unsigned int *hfmax;                               // [B][K]     bits of max softplus (>= 0, so ordered as uint)
     unsigned long long *key;                           // [B][K]     (ordered raw bits << 32) | ~flat index
     int B, D, K, KC, NOUT, NT, total_tiles, NS;
@@ -156,8 +158,8 @@ tc_head_centroid_kernel(const HeadLaunch L)
                     }
                     if (lane == 0) {
                         const size_t e = (size_t)b * L.K + k0 + i;
-                        atomicAdd(L.sums + 4 * e + 0, a); atomicAdd(L.sums + 4 * e + 1, bx);
-                        atomicAdd(L.sums + 4 * e + 2, by); atomicAdd(L.sums + 4 * e + 3, bz);
+                        const size_t slot = (size_t)(((int)blockIdx.x + b) * 4 + q);
+                        reinterpret_cast<float4 *>(L.sums)[slot * L.K + k0 + i] = make_float4(a, bx, by, bz);
                         atomicMax(L.hfmax + e, __float_as_uint(hm));
                         atomicMax(L.key + e, ky);
                     }
@@ -212,25 +214,42 @@ tc_head_centroid_kernel(const HeadLaunch L)
     }
 }
 
-// accumulators -> points3D (mm), confidences, argmax   (model.py:84-87)
+// accumulators -> points3D (mm), confidences, argmax   (model.py:84-87).  One warp per (frame set, key point): the
+// lanes stride over the frame set's slots in CTA order, then a fixed shuffle tree: deterministic, fp64.
 __global__ void centroid_finalize_kernel(const float *__restrict__ sums, const unsigned int *__restrict__ hfmax,
                                          const unsigned long long *__restrict__ key, int BK, int K, float spacing, float roi,
-                                         const int32_t *__restrict__ center3D, float *__restrict__ points, float *__restrict__ conf,
-                                         int32_t *__restrict__ argmax)
+                                         const float *__restrict__ center3D, float *__restrict__ points, float *__restrict__ conf,
+                                         int32_t *__restrict__ argmax, int grid, int Tb, long long T)
 {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (o >= BK) return;
-    const int b = o / K;
-    const float n = sums[4 * o], sx = sums[4 * o + 1], sy = sums[4 * o + 2], sz = sums[4 * o + 3];
+    const int b = o / K, k = o - b * K;
+    const int c0 = stat_owner((long long)b * Tb, grid, T), c1 = stat_owner((long long)(b + 1) * Tb - 1, grid, T);
+    const float4 *src = reinterpret_cast<const float4 *>(sums) + (size_t)(c0 + b) * 4 * K + k;
+    double dn = 0.0, dx = 0.0, dy = 0.0, dz = 0.0;
+    for (int s = lane; s < (c1 - c0 + 1) * 4; s += 32) {
+        // a warp (quadrant q, key-point half) only flushes the key points it owns, and only rows it saw: every slot of
+        // every CTA in [c0, c1] is written for every key point, because all 8 epilogue warps flush at a frame-set change
+        const float4 v = src[(size_t)s * K];
+        dn += (double)v.x; dx += (double)v.y; dy += (double)v.z; dz += (double)v.w;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        dn += __shfl_xor_sync(0xffffffffu, dn, s); dx += __shfl_xor_sync(0xffffffffu, dx, s);
+        dy += __shfl_xor_sync(0xffffffffu, dy, s); dz += __shfl_xor_sync(0xffffffffu, dz, s);
+    }
+    if (lane != 0) return;
+    const float n = (float)dn, sx = (float)dx, sy = (float)dy, sz = (float)dz;
     conf[o] = fminf(__uint_as_float(hfmax[o]), 255.f) / 255.f;
     if (argmax) argmax[o] = (int32_t)(0xffffffffu - (unsigned int)(key[o] & 0xffffffffull));
     const float sc = spacing * 2.f, half = roi / 2.f;
-    points[3 * o + 0] = (sx / n) * sc - half + (float)center3D[3 * b + 0];
-    points[3 * o + 1] = (sy / n) * sc - half + (float)center3D[3 * b + 1];
-    points[3 * o + 2] = (sz / n) * sc - half + (float)center3D[3 * b + 2];
+    points[3 * o + 0] = (sx / n) * sc - half + center3D[3 * b + 0];
+    points[3 * o + 1] = (sy / n) * sc - half + center3D[3 * b + 1];
+    points[3 * o + 2] = (sz / n) * sc - half + center3D[3 * b + 2];
 }
 
-size_t head_acc_bytes(int B, int K) { return align_up((size_t)B * K * 4 * 4, 256) + align_up((size_t)B * K * 4, 256) + align_up((size_t)B * K * 8, 256); }
+static size_t head_sum_bytes(int B, int K) { return align_up((size_t)stat_slots(256, B) * K * 16, 256); }
+size_t head_acc_bytes(int B, int K) { return head_sum_bytes(B, K) + align_up((size_t)B * K * 4, 256) + align_up((size_t)B * K * 8, 256); }
 
 static size_t head_smem(int KC, int NOUT, int NS)
 {
@@ -241,15 +260,16 @@ bool head_supported(int K, int cin_pad, int cout_pad, int D) { return K <= 2 * H
 
 // in: BP bf16 activations of decoder output; acc: head_acc_bytes() of scratch.  Launches memset + GEMM/centroid + finalize.
 int head_centroid_launch(const void *in, const __nv_bfloat16 *w, const float *bias, int B, int D, int K, int cin_pad, int cout_pad,
-                         float spacing, float roi, const int32_t *center3D, float *points, float *conf, int32_t *argmax, void *acc,
+                         float spacing, float roi, const float *center3D, float *points, float *conf, int32_t *argmax, void *acc,
                          int sms, int max_smem, cudaStream_t st)
 {
     HeadLaunch L;
     L.in = (const uint4 *)in; L.w = w; L.bias = bias; L.B = B; L.D = D; L.K = K; L.KC = cin_pad / 8; L.NOUT = cout_pad;
     char *p = (char *)acc;
-    L.sums = (float *)p; p += align_up((size_t)B * K * 4 * 4, 256);
+    L.sums = (float *)p; p += head_sum_bytes(B, K);
     L.hfmax = (unsigned int *)p; p += align_up((size_t)B * K * 4, 256);
     L.key = (unsigned long long *)p;
+    if (sms > 256) return fail(JHN_ERR_ARCH, "device has %d SMs; the partial-sum slots are sized for <= 256", sms);
     const int Wp = D + 2;
     L.NT = cdiv((long long)(D - 1) * Wp + D, TILE_M);
     L.total_tiles = B * D * L.NT;
@@ -258,7 +278,7 @@ int head_centroid_launch(const void *in, const __nv_bfloat16 *w, const float *bi
     if (head_smem(L.KC, L.NOUT, ns) > (size_t)max_smem) return fail(JHN_ERR_SHAPE, "fused head: tile does not fit shared memory");
     L.NS = ns;
     const size_t smem = head_smem(L.KC, L.NOUT, ns);
-    JHN_CUDA(cudaMemsetAsync(acc, 0, head_acc_bytes(B, K), st));
+    JHN_CUDA(cudaMemsetAsync((char *)acc + head_sum_bytes(B, K), 0, head_acc_bytes(B, K) - head_sum_bytes(B, K), st));   // the two maxima
     static int configured_dev = -1;
     int dev = 0;
     JHN_CUDA(cudaGetDevice(&dev));
@@ -270,8 +290,8 @@ int head_centroid_launch(const void *in, const __nv_bfloat16 *w, const float *bi
     JHN_LAUNCH("tc_head_centroid_kernel", st, tc_head_centroid_kernel<<<grid, HD_THREADS, smem, st>>>(L));
     const int BK = B * K;
     JHN_LAUNCH("centroid_finalize_kernel", st,
-               centroid_finalize_kernel<<<cdiv(BK, 128), 128, 0, st>>>(L.sums, L.hfmax, L.key, BK, K, spacing, roi, center3D, points,
-                                                                       conf, argmax));
+               centroid_finalize_kernel<<<cdiv(BK, 4), 128, 0, st>>>(L.sums, L.hfmax, L.key, BK, K, spacing, roi, center3D, points,
+                                                                     conf, argmax, grid, D * L.NT, (long long)L.total_tiles));
     return JHN_OK;
 }
 

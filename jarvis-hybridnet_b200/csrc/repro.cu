@@ -24,6 +24,8 @@
 //   gather_stream_kernel   (bf16 throughput path) the same arithmetic as a persistent, warp-specialised kernel:
 //                          pixel boxes of a channels-last fp16 staging copy are TMA-staged in shared memory and
 //                          gathered with LDS.128; see the block comment above the kernel.
+#include <atomic>
+
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -44,7 +46,7 @@ __device__ __forceinline__ float lerp_rn(float w0, float a, float w1, float b, i
 constexpr int CP_PARAMS = 20;                           // P[12], fx, fy, cx, cy, k1, k2, chx, chy
 __global__ void __launch_bounds__(256)
 coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ intr,
-                      const float *__restrict__ dist, const int32_t *__restrict__ center3D,
+                      const float *__restrict__ dist, const float *__restrict__ center3D,
                       const int32_t *__restrict__ centerHM, int B, int ncam, int h, float spacing, int hs,
                       float2 *__restrict__ cab, int *__restrict__ roi)
 {
@@ -75,9 +77,9 @@ coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ i
     const int half = h / 2;
     const float fhs = (float)hs, fhs1 = (float)(hs - 1), fhs2 = (float)(hs - 2);
     // grid = (idx - half) * spacing * 2 + center        repro_layer.py:32-36,113
-    const float X = __fadd_rn(__fmul_rn(__fmul_rn((float)(i - half), spacing), 2.f), (float)center3D[3 * b + 0]);
-    const float Y = __fadd_rn(__fmul_rn(__fmul_rn((float)(j - half), spacing), 2.f), (float)center3D[3 * b + 1]);
-    const float Z = __fadd_rn(__fmul_rn(__fmul_rn((float)(k - half), spacing), 2.f), (float)center3D[3 * b + 2]);
+    const float X = __fadd_rn(__fmul_rn(__fmul_rn((float)(i - half), spacing), 2.f), center3D[3 * b + 0]);
+    const float Y = __fadd_rn(__fmul_rn(__fmul_rn((float)(j - half), spacing), 2.f), center3D[3 * b + 1]);
+    const float Z = __fadd_rn(__fmul_rn(__fmul_rn((float)(k - half), spacing), 2.f), center3D[3 * b + 2]);
 #pragma unroll 4
     for (int c = 0; c < ncam; ++c) {
         const float *P = cp + c * CP_PARAMS;
@@ -153,6 +155,35 @@ __device__ __forceinline__ void add8(const __nv_bfloat16 *p, float *acc)
     }
 }
 
+__device__ __forceinline__ void add8(const __half *p, float *acc)
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                       // staged values carry the exact factor 2^-4
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+        acc[2 * i + 0] += f.x * HALF_STAGE_UNSCALE;
+        acc[2 * i + 1] += f.y * HALF_STAGE_UNSCALE;
+    }
+}
+
+// bf16 channels-last -> the streaming gather's fp16 staging format (x 2^-4), 16 bytes per thread
+__global__ void __launch_bounds__(256)
+bf16cl_to_f16cl_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n16)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    const uint4 v = __ldg(in + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __half2 h = __floats2half2_rn(__uint_as_float(w[k] << 16) * HALF_STAGE_SCALE, __uint_as_float(w[k] & 0xffff0000u) * HALF_STAGE_SCALE);
+        o[k] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // planar -> channels-last: one thread per padded pixel reads its K channel values (for a fixed channel the lanes
 // of a warp read consecutive floats: coalesced, K independent loads in flight per thread); the 16-bit staging
 // copy goes through a per-warp shared-memory tile so that each store instruction writes 512 contiguous bytes.
@@ -214,8 +245,18 @@ static int launch_relayout(const ReprojectArgs &a, T *hm_cl, const int4 *roi, cu
 {
     const long long npix = (long long)a.B * a.ncam * a.hs * a.hs;
     JHN_LAUNCH("relayout_kernel", st,
-               relayout_pixel_kernel<T><<<cdiv(npix, 256), 256, 0, st>>>(a.heatmaps, a.K, a.hs, a.padded, npix, roi, hm_cl));
+               relayout_pixel_kernel<T><<<cdiv(npix, 256), 256, 0, st>>>((const float *)a.heatmaps, a.K, a.hs, a.padded, npix, roi, hm_cl));
     return JHN_OK;
+}
+
+// jhn_heatmap_convert: whole maps, no pixel-box restriction (the caller may gather any grid from the result)
+int heatmap_convert_launch(const float *hm, int padded, int B, int ncam, int K, int hs, int dst_format, void *dst, cudaStream_t st)
+{
+    ReprojectArgs a{};
+    a.heatmaps = hm; a.hm_format = JHN_HM_F32_PLANAR; a.padded = padded; a.B = B; a.ncam = ncam; a.K = K; a.hs = hs;
+    if (dst_format == JHN_HM_F16_CL) return launch_relayout<__half>(a, (__half *)dst, nullptr, st);
+    if (dst_format == JHN_HM_BF16_CL) return launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)dst, nullptr, st);
+    return fail(JHN_ERR_ARG, "jhn_heatmap_convert: dst_format %d is not a channels-last format", dst_format);
 }
 
 constexpr int TS = 8;                                   // voxel tile side
@@ -713,11 +754,12 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
 }
 
 constexpr int GS_CAP = 15360;                                                  // bytes per pixel-box slot of the streaming kernel
-static int g_box_limit = GS_CAP;                                               // boxes above this gather from global memory (test hook)
+static std::atomic<int> g_box_limit{GS_CAP};                                   // boxes above this gather from global memory (test hook)
 int gather_set_box_bytes(int bytes)
 {
-    g_box_limit = (bytes <= 0 || bytes > GS_CAP) ? GS_CAP : bytes;
-    return g_box_limit;
+    const int v = (bytes <= 0 || bytes > GS_CAP) ? GS_CAP : bytes;
+    g_box_limit.store(v, std::memory_order_relaxed);
+    return v;
 }
 
 template <int LAYOUT>
@@ -727,22 +769,20 @@ static int launch_stream(const ReprojectArgs &a, const __half *hm_cl, const floa
     const int nt = a.G / GT + 1, ntk = a.G / GT;
     const long long total = (long long)a.B * nt * nt * ntk;
     if (total * a.ncam > 0x7fffffffLL) return fail(JHN_ERR_SHAPE, "too many gather tiles (%lld)", total);
-    static int ctas = 0;                                                        // 3 resident CTAs per SM
-    if (!ctas) {
-        int dev = 0, sms = 0;
-        JHN_CUDA(cudaGetDevice(&dev));
-        JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        ctas = 3 * sms;
-    }
+    int dev = 0, sms = 0;                                                       // 3 resident CTAs per SM
+    JHN_CUDA(cudaGetDevice(&dev));
+    JHN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ctas = 3 * sms;
     const int grid = (int)(total < ctas ? total : ctas);
     const float post_scale = HALF_STAGE_UNSCALE / ((float)a.ncam * a.post_divide);
+    const int box_limit = g_box_limit.load(std::memory_order_relaxed);
 #define JHN_STREAM(MODE)                                                                                         \
     {                                                                                                            \
         auto kern = gather_stream_kernel<LAYOUT, MODE>;                                                          \
         JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));           \
         JHN_LAUNCH("gather_stream_kernel", st,                                                                   \
                    kern<<<grid, GS_THREADS, gsmem, st>>>(hm_cl, cab, a.ncam, a.K, a.hs, a.G, post_scale, cap, \
-                                                         g_box_limit, a.volume_out, (int)total));                              \
+                                                         box_limit, a.volume_out, (int)total));                              \
         return JHN_OK;                                                                                           \
     }
     if (a.lerp_mode == JHN_LERP_FMA_FIRST) JHN_STREAM(JHN_LERP_FMA_FIRST)
@@ -757,7 +797,7 @@ size_t reproject_workspace(int B, int ncam, int K, int hs, int G, int precision)
     const int h = G / 2;
     Arena a(nullptr, 0);
     a.take<float2>((size_t)B * ncam * h * h * h);                   // coarse (x, y) pixel coordinates
-    const size_t px = (size_t)B * ncam * hs * hs * KP;
+    const size_t px = (size_t)B * ncam * hs * hs * KP;              // staging copy (not touched when the caller hands JHN_HM_F16_CL)
     if (precision == JHN_FP32) a.take<float>(px); else a.take<__nv_bfloat16>(px);
     a.take<int4>((size_t)B * ncam);                                 // per-camera pixel box of the voxel grid
     return a.off;
@@ -799,23 +839,35 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
     void *hm_cl = (a.precision == JHN_FP32) ? (void *)ar.take<float>(px) : (void *)ar.take<__nv_bfloat16>(px);
     int4 *roi = ar.take<int4>((size_t)a.B * a.ncam);
     if (!ar.ok()) return fail(JHN_ERR_WORKSPACE, "reproject workspace: need %zu bytes, got %zu", ar.off, ws_bytes);
+    const bool planar = a.hm_format == JHN_HM_F32_PLANAR;
+    if (!planar && (a.precision == JHN_FP32 || !a.padded))
+        return fail(JHN_ERR_ARG, "channels-last heat maps are a 16-bit, padded format: they need precision JHN_BF16 and heatmaps_padded = 1");
 
     // the streaming gather's staging copy covers only each camera's pixel box of the voxel grid (collected by the
     // projection kernel); the other paths relayout whole maps
     const bool stream = a.precision != JHN_FP32 && !a.index_out && a.G % GT == 0;
-    if (stream) JHN_CUDA(cudaMemsetAsync(roi, 0x7f, (size_t)a.B * a.ncam * sizeof(int4), st));
+    const bool want_roi = stream && planar;
+    if (want_roi) JHN_CUDA(cudaMemsetAsync(roi, 0x7f, (size_t)a.B * a.ncam * sizeof(int4), st));
     JHN_LAUNCH("coarse_project_kernel", st,
                coarse_project_kernel<<<dim3(cdiv((long long)h * h * h, 256), a.B), 256,
                                        a.ncam * (CP_PARAMS * sizeof(float) + 4 * sizeof(int)), st>>>(
-                   a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B, a.ncam, h, a.spacing, a.hs, cab, stream ? (int *)roi : nullptr));
+                   a.cam, a.intr, a.dist, a.center3D, a.centerHM, a.B, a.ncam, h, a.spacing, a.hs, cab, want_roi ? (int *)roi : nullptr));
     if (a.precision == JHN_FP32) {
         JHN_TRY(launch_relayout<float>(a, (float *)hm_cl, nullptr, st));
         return run_gather<float>(a, (const float *)hm_cl, cab, st);
     }
     if (stream) {
-        // throughput path: fp16 staging copy + streaming gather (the index dump needs the in-order kernel below)
-        JHN_TRY(launch_relayout<__half>(a, (__half *)hm_cl, roi, st));
-        if (a.layout == JHN_VOL_NCDHW_F32) return launch_stream<JHN_VOL_NCDHW_F32>(a, (const __half *)hm_cl, cab, GS_CAP, st);
+        // throughput path: fp16 staging copy + streaming gather (the index dump needs the in-order kernel below).
+        // JHN_HM_F16_CL is that staging format: gathered in place, no copy at all.
+        const __half *src16 = (const __half *)hm_cl;
+        if (planar) JHN_TRY(launch_relayout<__half>(a, (__half *)hm_cl, roi, st));
+        else if (a.hm_format == JHN_HM_F16_CL) src16 = (const __half *)a.heatmaps;
+        else {
+            const size_t n16 = px / 8;
+            JHN_LAUNCH("relayout_kernel", st,
+                       bf16cl_to_f16cl_kernel<<<cdiv((long long)n16, 256), 256, 0, st>>>((const uint4 *)a.heatmaps, (uint4 *)hm_cl, n16));
+        }
+        if (a.layout == JHN_VOL_NCDHW_F32) return launch_stream<JHN_VOL_NCDHW_F32>(a, src16, cab, GS_CAP, st);
         const int CJ = (a.K + 15) / 16 * 2;
         if (!a.borders_valid) {
             JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
@@ -825,8 +877,10 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
                                            (CJ - KP / 8) * chunk_bytes, (size_t)a.B * 8, st));
             }
         }
-        return launch_stream<JHN_VOL_V2V_BF16>(a, (const __half *)hm_cl, cab, GS_CAP, st);
+        return launch_stream<JHN_VOL_V2V_BF16>(a, src16, cab, GS_CAP, st);
     }
+    if (a.hm_format == JHN_HM_F16_CL) return run_gather<__half>(a, (const __half *)a.heatmaps, cab, st);
+    if (a.hm_format == JHN_HM_BF16_CL) return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)a.heatmaps, cab, st);
     JHN_TRY(launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)hm_cl, nullptr, st));
     return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)hm_cl, cab, st);
 }

@@ -17,7 +17,7 @@ __device__ __forceinline__ void tail_merge(TailAcc &a, const TailAcc &b)
 
 __global__ void __launch_bounds__(256)
 centroid_kernel(const float *__restrict__ v, int K, int h, float spacing, float roi,
-                const int32_t *__restrict__ center3D, float *__restrict__ points, float *__restrict__ conf,
+                const float *__restrict__ center3D, float *__restrict__ points, float *__restrict__ conf,
                 int32_t *__restrict__ argmax)
 {
     const int k = blockIdx.x, b = blockIdx.y;
@@ -55,13 +55,13 @@ centroid_kernel(const float *__restrict__ v, int K, int h, float spacing, float 
         conf[o] = fminf(t.hf_max, 255.f) / 255.f;                    // :84-85
         if (argmax) argmax[o] = t.arg;
         const float sc = spacing * 2.f, half = roi / 2.f;            // :86-87
-        points[3 * o + 0] = (t.sx / t.n) * sc - half + (float)center3D[3 * b + 0];
-        points[3 * o + 1] = (t.sy / t.n) * sc - half + (float)center3D[3 * b + 1];
-        points[3 * o + 2] = (t.sz / t.n) * sc - half + (float)center3D[3 * b + 2];
+        points[3 * o + 0] = (t.sx / t.n) * sc - half + center3D[3 * b + 0];
+        points[3 * o + 1] = (t.sy / t.n) * sc - half + center3D[3 * b + 1];
+        points[3 * o + 2] = (t.sz / t.n) * sc - half + center3D[3 * b + 2];
     }
 }
 
-int centroid_launch(const float *v, int B, int K, int h, float spacing, float roi, const int32_t *center3D,
+int centroid_launch(const float *v, int B, int K, int h, float spacing, float roi, const float *center3D,
                     float *points, float *conf, int32_t *argmax, cudaStream_t st)
 {
     JHN_LAUNCH("centroid_kernel", st,

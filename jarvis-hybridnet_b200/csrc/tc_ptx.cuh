@@ -7,6 +7,24 @@ namespace jhn {
 constexpr int TILE_M = 128;                           // GEMM rows (positions) per tcgen05.mma
 
 // ------------------------------------------------------------------------------------------------
+// Deterministic InstanceNorm statistics.  Every persistent conv kernel gives CTA c the contiguous tile range
+// [T*c/grid, T*(c+1)/grid) and tiles are sample-major (Tb tiles per sample), so the CTAs that touch sample b are the
+// consecutive range owner(b*Tb) .. owner((b+1)*Tb - 1).  Each of them writes its per-quadrant partial sums of the
+// sample to a slot of its own,  part[4 * (c + b) + quadrant][channel][sum, sumsq]  (c + b is unique along the
+// staircase of (CTA, sample) pairs; plain stores, no atomics, 4 * (grid + B) slots), and the consumer adds the
+// slots of its sample in CTA order in fp64: the same bits on every run.
+// ------------------------------------------------------------------------------------------------
+struct StatPart {
+    float *part;                                      // [4 * (grid + B)][NOUT][2] or null
+    int grid; int Tb; long long T;                    // launch geometry of the producing kernel
+};
+__host__ __device__ __forceinline__ int stat_owner(long long t, int grid, long long T)
+{
+    return (int)(((t + 1) * grid + T - 1) / T) - 1;   // the CTA whose range contains tile t
+}
+static inline int stat_slots(int sms, int B) { return 4 * (sms + B); }
+
+// ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

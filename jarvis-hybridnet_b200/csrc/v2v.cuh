@@ -1,5 +1,7 @@
 // Packed V2VNet weights (opaque to callers as `jhn_v2v`) and the two forward paths.
 #pragma once
+#include <mutex>
+
 #include "common.cuh"
 
 namespace jhn {
@@ -27,18 +29,37 @@ struct jhn_v2v {
     jhn::TcNet *tc;          // non-null iff precision == JHN_BF16
     // Zero-border cache (jhn_v2v_set_workspace_persistent): the padded bf16 tensors keep their zero borders from
     // one forward to the next because every kernel writes zeros (or nothing) there, so they are cleared only
-    // when the workspace pointer or the shape changes.  Off by default: the caller must promise that nobody
-    // else writes the workspace between calls.
+    // when a workspace is first seen or its shape changes.  Off by default: the caller must promise that nobody
+    // else writes the workspace between calls.  The cache is a small table keyed by workspace pointer behind a
+    // mutex, so one handle may serve several streams / threads as long as each has its own workspace.
+    mutable std::mutex mu;
     mutable int ws_persistent;
-    mutable const void *z_ws; mutable int z_B, z_G, z_kind;       // tensors of tc_forward
-    mutable const void *zv_ptr; mutable int zv_B, zv_G;           // V2V-layout volume written by the reprojection stage
+    struct BorderKey { const void *ptr; int B, G, kind; };
+    mutable BorderKey zc[16];
+    mutable int zc_n;
+    // true iff the borders of the tensors carved from `ptr` for (B, G, kind) are already zero; records the key otherwise
+    bool borders_cached(const void *ptr, int B, int G, int kind) const
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!ws_persistent) return false;
+        for (int i = 0; i < zc_n; ++i)
+            if (zc[i].ptr == ptr && zc[i].kind / 16 == kind / 16) {
+                const bool ok = zc[i].B == B && zc[i].G == G && zc[i].kind == kind;
+                zc[i].B = B; zc[i].G = G; zc[i].kind = kind;
+                return ok;
+            }
+        if (zc_n == 16) zc_n = 0;                                // table full: forget everything (costs one re-zeroing each)
+        zc[zc_n++] = BorderKey{ptr, B, G, kind};
+        return false;
+    }
+    void borders_forget() const { std::lock_guard<std::mutex> g(mu); zc_n = 0; }
 };
 
 namespace jhn {
 // centroid tail fused into the bf16 output layer (head_tc.cu); `acc` is head_acc_bytes(B, K) of scratch
 struct TailArgs {
     float spacing, roi;
-    const int32_t *center3D;
+    const float *center3D;
     float *points, *conf;
     int32_t *argmax;
     void *acc;

@@ -24,16 +24,16 @@ from .v2vnet import V2VNet
 
 def centroid_tail(v2v_out, spacing, roi, center3D, want_argmax=False):
     """model.py:73-87 on [B,K,h,h,h] fp32 -> points3D [B,K,3] (mm), confidences [B,K] (, argmax [B,K])."""
-    _lib.require_cuda(v2v_out, center3D)
     lib = _lib.load()
-    B, K, h = v2v_out.shape[0], v2v_out.shape[1], v2v_out.shape[2]
-    v = v2v_out.contiguous().float()
-    c3 = center3D.contiguous().to(torch.int32)
-    pts = torch.empty((B, K, 3), dtype=torch.float32, device=v.device)
-    conf = torch.empty((B, K), dtype=torch.float32, device=v.device)
-    am = torch.empty((B, K), dtype=torch.int32, device=v.device)
-    _lib.check(lib.jhn_centroid_reduce(_lib.dptr(v), B, K, h, float(spacing), float(roi), _lib.dptr(c3),
-                                       _lib.dptr(pts), _lib.dptr(conf), _lib.dptr(am), _lib.stream_ptr()))
+    with _lib.require_cuda(v2v_out, center3D):
+        B, K, h = v2v_out.shape[0], v2v_out.shape[1], v2v_out.shape[2]
+        v = v2v_out.contiguous().float()
+        c3 = center3D.contiguous().float()               # `+ center3D` of model.py:86-87 promotes an int centre to fp32
+        pts = torch.empty((B, K, 3), dtype=torch.float32, device=v.device)
+        conf = torch.empty((B, K), dtype=torch.float32, device=v.device)
+        am = torch.empty((B, K), dtype=torch.int32, device=v.device)
+        _lib.check(lib.jhn_centroid_reduce(_lib.dptr(v), B, K, h, float(spacing), float(roi), _lib.dptr(c3),
+                                           _lib.dptr(pts), _lib.dptr(conf), _lib.dptr(am), _lib.stream_ptr()))
     return (pts, conf, am) if want_argmax else (pts, conf)
 
 
@@ -97,35 +97,44 @@ class HybridNet3D(nn.Module):
         self._graphs = {}
 
     def forward(self, heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients, _ws=None):
-        _lib.require_cuda(heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients)
+        """heatmaps: fp32 planar [B,ncam,K,S,S] (the reference's tensor), or the gather-native channels-last form
+        [B,ncam,hs,hs,24] in torch.float16 (scaled by 1/16, `_lib.heatmap_convert`) / torch.bfloat16."""
         lib = _lib.load()
-        B, ncam, K, S, _ = heatmaps.shape
-        if K != self.K or S not in (self.hs, self.hs - 2):
-            raise RuntimeError(f"heat maps {tuple(heatmaps.shape)} do not match K={self.K}, hs={self.hs}")
-        net = self.v2vNet._get_handle()
-        need = _lib.c_size_t()
-        _lib.check(lib.jhn_hybrid3d_workspace_bytes(net, B, ncam, self.hs, self.G, need))
-        if _ws is not None:                                  # a captured graph owns its workspace
-            ws = _ws
-            if ws.numel() < need.value:
-                raise RuntimeError("graph workspace too small")
-        else:
-            if self._ws is None or self._ws.numel() < need.value or self._ws.device != heatmaps.device:
-                self._ws = torch.empty(need.value, dtype=torch.uint8, device=heatmaps.device)
-            ws = self._ws
-        dev = heatmaps.device
-        pts = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
-        conf = torch.empty((B, K), dtype=torch.float32, device=dev)
-        am = torch.empty((B, K), dtype=torch.int32, device=dev)
-        f = lambda t: t.contiguous().float()
-        i = lambda t: t.contiguous().to(torch.int32)
-        hm, cam, intr, dist, c3, chm = f(heatmaps), f(cameraMatrices), f(intrinsicMatrices), \
-            f(distortionCoefficients), i(center3D), i(centerHM)
-        _lib.check(lib.jhn_hybrid3d_forward(net, _lib.dptr(hm), int(S == self.hs), _lib.dptr(cam), _lib.dptr(intr),
-                                            _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm), B, ncam, self.hs, self.G,
-                                            float(self.spacing), float(self.roi), self.lerp_mode, _lib.dptr(pts),
-                                            _lib.dptr(conf), _lib.dptr(am), _lib.dptr(ws), ws.numel(),
-                                            _lib.stream_ptr()))
+        with _lib.require_cuda(heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients):
+            if heatmaps.dtype in (torch.float16, torch.bfloat16):
+                B, ncam, S, S2, P = heatmaps.shape
+                if (S, S2, P) != (self.hs, self.hs, _lib.HM_CL_PITCH):
+                    raise RuntimeError(f"channels-last heat maps {tuple(heatmaps.shape)} do not match [B,ncam,{self.hs},{self.hs},24]")
+                fmt = _lib.HM_F16_CL if heatmaps.dtype == torch.float16 else _lib.HM_BF16_CL
+                hm, K = heatmaps.contiguous(), self.K
+            else:
+                B, ncam, K, S, _ = heatmaps.shape
+                if K != self.K or S not in (self.hs, self.hs - 2):
+                    raise RuntimeError(f"heat maps {tuple(heatmaps.shape)} do not match K={self.K}, hs={self.hs}")
+                fmt, hm = _lib.HM_F32_PLANAR, heatmaps.contiguous().float()
+            net = self.v2vNet._get_handle()
+            need = _lib.c_size_t()
+            _lib.check(lib.jhn_hybrid3d_workspace_bytes(net, B, ncam, self.hs, self.G, need))
+            if _ws is not None:                                  # a captured graph owns its workspace
+                ws = _ws
+                if ws.numel() < need.value:
+                    raise RuntimeError("graph workspace too small")
+            else:
+                if self._ws is None or self._ws.numel() < need.value or self._ws.device != heatmaps.device:
+                    self._ws = torch.empty(need.value, dtype=torch.uint8, device=heatmaps.device)
+                ws = self._ws
+            dev = heatmaps.device
+            pts = torch.empty((B, K, 3), dtype=torch.float32, device=dev)
+            conf = torch.empty((B, K), dtype=torch.float32, device=dev)
+            am = torch.empty((B, K), dtype=torch.int32, device=dev)
+            f = lambda t: t.contiguous().float()
+            cam, intr, dist, c3 = f(cameraMatrices), f(intrinsicMatrices), f(distortionCoefficients), f(center3D)
+            chm = centerHM.contiguous().to(torch.int32)
+            _lib.check(lib.jhn_hybrid3d_forward(net, _lib.dptr(hm), fmt, int(S == self.hs), _lib.dptr(cam), _lib.dptr(intr),
+                                                _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm), B, ncam, self.hs, self.G,
+                                                float(self.spacing), float(self.roi), self.lerp_mode, _lib.dptr(pts),
+                                                _lib.dptr(conf), _lib.dptr(am), _lib.dptr(ws), ws.numel(),
+                                                _lib.stream_ptr()))
         return pts, conf, am
 
     def workspace_bytes(self, B, ncam):
@@ -142,8 +151,9 @@ class HybridNet3D(nn.Module):
         static outputs: consume them before the next call with the same signature."""
         ins = (heatmaps, center3D, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients)
         _lib.require_cuda(*ins)
-        dts = (torch.float32, torch.int32, torch.int32, torch.float32, torch.float32, torch.float32)
-        key = (tuple(tuple(t.shape) for t in ins), heatmaps.device)
+        dts = (heatmaps.dtype if heatmaps.dtype in (torch.float16, torch.bfloat16) else torch.float32, torch.float32,
+               torch.int32, torch.float32, torch.float32, torch.float32)
+        key = (tuple(tuple(t.shape) for t in ins), heatmaps.dtype, heatmaps.device)
         ent = self._graphs.get(key)
         if ent is None:
             B, ncam = heatmaps.shape[0], heatmaps.shape[1]

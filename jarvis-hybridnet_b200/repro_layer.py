@@ -45,15 +45,20 @@ class ReprojectionLayer(nn.Module):
 
     def _run(self, heatmaps, center, centerHM, cam, intr, dist, post_divide=1.0, want_index=False):
         """heatmaps [B,ncam,K,S,S] with S == heatmap_size (padded) or heatmap_size-2 (un-padded)."""
-        _lib.require_cuda(heatmaps, center, centerHM, cam, intr, dist)
         lib = _lib.load()
+        with _lib.require_cuda(heatmaps, center, centerHM, cam, intr, dist):
+            return self._run_on_device(lib, heatmaps, center, centerHM, cam, intr, dist, post_divide, want_index)
+
+    def _run_on_device(self, lib, heatmaps, center, centerHM, cam, intr, dist, post_divide, want_index):
         B, ncam, K, S, S2 = heatmaps.shape
         hs, G = self.heatmap_size, self.grid_size
         if S != S2 or S not in (hs, hs - 2):
             raise RuntimeError(f"heat maps are {S}x{S2}; expected {hs} (padded) or {hs - 2} per side")
         hm = heatmaps.contiguous().float()
         cam = cam.contiguous().float(); intr = intr.contiguous().float(); dist = dist.contiguous().float()
-        c3 = center.contiguous().to(torch.int32); chm = centerHM.contiguous().to(torch.int32)
+        # `self.grid + center[0]` (repro_layer.py:113) is an fp32 add: an int centre (predictor, jarvis3D.py:183) is
+        # promoted exactly, a float centre (validation path, hybridnet.py:284-304) is taken as it is — never truncated
+        c3 = center.contiguous().float(); chm = centerHM.contiguous().to(torch.int32)
         if cam.shape[:2] != (B, ncam) or chm.shape != (B, ncam, 2) or c3.shape != (B, 3):
             raise RuntimeError("calibration / centre tensors do not match heat maps [B,ncam,...]")
         need = _lib.c_size_t()
@@ -61,7 +66,7 @@ class ReprojectionLayer(nn.Module):
         ws = self._workspace(need.value, hm.device)
         vol = torch.empty((B, K, G, G, G), dtype=torch.float32, device=hm.device)
         idx = torch.empty((B, ncam, G, G, G), dtype=torch.int32, device=hm.device) if want_index else None
-        _lib.check(lib.jhn_reproject_gather(_lib.dptr(hm), int(S == hs), _lib.dptr(cam), _lib.dptr(intr),
+        _lib.check(lib.jhn_reproject_gather(_lib.dptr(hm), _lib.HM_F32_PLANAR, int(S == hs), _lib.dptr(cam), _lib.dptr(intr),
                                             _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm), B, ncam, K, hs, G,
                                             float(self.grid_spacing), self.lerp_mode, float(post_divide),
                                             self.precision, _lib.VOL_NCDHW_F32, _lib.dptr(vol), _lib.dptr(idx),
@@ -72,7 +77,7 @@ class ReprojectionLayer(nn.Module):
         """int64 [ncam,G,G,G] flat padded-pixel indices, as repro_layer.py:40-85.  `x` is `self.grid + center`
         like the reference passes; the integer centre is read back from its zero voxel."""
         half = int(self.grid_size / 2 / 2)
-        center = x[half, half, half].round().to(torch.int32)[None]
+        center = x[half, half, half].float()[None]             # grid[half,half,half] == 0, so this is the centre itself
         ncam = cameraMatrices.shape[0]
         dummy = torch.zeros((1, ncam, 1, self.heatmap_size, self.heatmap_size), device=x.device)
         _, idx = self._run(dummy, center, centerHM[None], cameraMatrices[None], intrinsicMatrices[None],

@@ -51,12 +51,14 @@ static inline void src_index(int dst, int h, int *i0, int *i1, float *l0, float 
 /* Coarse projection: a,b of SURVEY.md §9.1 for every coarse grid point and camera.
  * coarse_a / coarse_b : [ncam][h][h][h] fp32 (x fastest = k index, as the reference's view). */
 static void project_coarse(const float *cam, const float *intr, const float *dist,
-                           const int32_t *center3D, const int32_t *centerHM,
+                           const float *center3D, const int32_t *centerHM,
                            int c_begin, int c_end, int h, float spacing, int hs,
                            float *coarse_a, float *coarse_b)
 {
     const int half = h / 2;                               /* int(grid_size/2/2), repro_layer.py:28 */
-    const float c3x = (float)center3D[0], c3y = (float)center3D[1], c3z = (float)center3D[2];
+    /* `self.grid + center[0]` (repro_layer.py:113): an int centre (jarvis3D.py:183) is promoted to fp32 (exact), a
+     * float centre (validation path, hybridnet.py:284-304) is added as it is */
+    const float c3x = center3D[0], c3y = center3D[1], c3z = center3D[2];
     for (int c = c_begin; c < c_end; ++c) {
         const float *P = cam + 12 * c;                    /* [4][3] row-major                      */
         const float fx = intr[9 * c + 0], fy = intr[9 * c + 4];
@@ -104,7 +106,7 @@ static void project_coarse(const float *cam, const float *intr, const float *dis
  * Optional outputs: coarse_a/coarse_b [ncam][h^3] (pre-interpolation coordinates).
  * Only cameras [c_begin,c_end) are written, so the Python wrapper can split cameras over threads. */
 int jho_reproject_indices(const float *cam, const float *intr, const float *dist,
-                          const int32_t *center3D, const int32_t *centerHM,
+                          const float *center3D, const int32_t *centerHM,
                           int ncam, int G, float spacing, int hs, int lerp_mode,
                           int32_t *idx_out, float *coarse_a_out, float *coarse_b_out,
                           int c_begin, int c_end)
@@ -177,7 +179,7 @@ int jho_gather_mean(const float *hm, const int32_t *idx, int ncam, int K, int hs
  * (model.py:73-87); argmax = first maximum of the raw volume ("argmax voxel").
  * v: [K][h][h][h] fp32 with axes (x=i, y=j, z=k) like the ij meshgrid of model.py:44-48.
  * Sums are accumulated in double so the oracle is the low-noise side of the 0.05 mm comparison. */
-int jho_centroid(const float *v, int K, int h, float spacing, float roi, const int32_t *center3D,
+int jho_centroid(const float *v, int K, int h, float spacing, float roi, const float *center3D,
                  float *points, float *conf, int32_t *argmax)
 {
     const size_t nv = (size_t)h * h * h;
@@ -200,9 +202,9 @@ int jho_centroid(const float *v, int K, int h, float spacing, float roi, const i
         argmax[k] = best;
         float cx = (float)(sx / n), cy = (float)(sy / n), cz = (float)(sz / n);
         /* points*spacing*2 - roi/2 + center3D  (model.py:86-87) */
-        points[3 * k + 0] = cx * spacing * 2.f - roi / 2.f + (float)center3D[0];
-        points[3 * k + 1] = cy * spacing * 2.f - roi / 2.f + (float)center3D[1];
-        points[3 * k + 2] = cz * spacing * 2.f - roi / 2.f + (float)center3D[2];
+        points[3 * k + 0] = cx * spacing * 2.f - roi / 2.f + center3D[0];
+        points[3 * k + 1] = cy * spacing * 2.f - roi / 2.f + center3D[1];
+        points[3 * k + 2] = cz * spacing * 2.f - roi / 2.f + center3D[2];
     }
     return 0;
 }

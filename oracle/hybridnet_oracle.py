@@ -38,8 +38,7 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()                                        # no-op unless the C source is newer than the library
         _lib = ctypes.CDLL(_SO)
     return _lib
 
@@ -77,7 +76,7 @@ def reproject_indices(center3D, centerHM, cameraMatrices, intrinsicMatrices, dis
     cam, intr, dist = _f32(cameraMatrices), _f32(intrinsicMatrices), _f32(distortionCoefficients)
     ncam = cam.shape[0]
     assert cam.shape == (ncam, 4, 3) and intr.shape == (ncam, 3, 3) and dist.shape == (ncam, 1, 5)
-    c3, chm = _i32(center3D).reshape(3), _i32(centerHM).reshape(ncam, 2)
+    c3, chm = _f32(center3D).reshape(3), _i32(centerHM).reshape(ncam, 2)
     h = G // 2
     idx = np.empty((ncam, G, G, G), np.int32)
     ca = np.empty((ncam, h, h, h), np.float32)
@@ -130,7 +129,7 @@ def centroid_tail(v, spacing, roi, center3D):
     conf = np.empty((K,), np.float32)
     am = np.empty((K,), np.int32)
     rc = lib().jho_centroid(_p(v), K, h, ctypes.c_float(spacing), ctypes.c_float(roi),
-                            _p(_i32(center3D).reshape(3)), _p(pts), _p(conf), _p(am))
+                            _p(_f32(center3D).reshape(3)), _p(pts), _p(conf), _p(am))
     if rc != 0:
         raise ValueError(f"jho_centroid rc={rc}")
     return pts, conf, am

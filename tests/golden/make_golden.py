@@ -121,9 +121,13 @@ def build_backbone(sh, v2v_sd):
 
 
 def run_case(name, sh, rig_seed, fs_seed, weights, full=True, chm_shift=None, sample=64, with_v2v=True,
-             idx_full=False):
+             idx_full=False, float_centre=False):
     cam, intr, dist = S.make_rig(sh.ncam, rig_seed)
     hm, c3, chm, kps = S.make_frameset(sh, cam, intr, dist, fs_seed)
+    if float_centre:
+        # the validation path hands the 3D network float centres int(c / spacing) * spacing (dataset3D via
+        # hybridnet.py:284-304): non-integer whenever GRID_SPACING is fractional
+        c3 = (np.trunc(c3.astype(np.float64) / sh.spacing) * sh.spacing + (0.5 * sh.spacing if float_centre == "half" else 0.0)).astype(np.float32)
     if chm_shift is not None:
         chm = (chm + np.asarray(chm_shift, np.int32)).astype(np.int32)
     out = dict(shape=np.array([sh.ncam, sh.K, sh.bbox, sh.roi, sh.spacing], np.float64),
@@ -154,8 +158,9 @@ def run_case(name, sh, rig_seed, fs_seed, weights, full=True, chm_shift=None, sa
             imgs = torch.zeros(1, sh.ncam, 3, 4, 4)
             hf, hpad, p3, conf = bb(imgs, torch.tensor([S.IMG_W, S.IMG_H]), t(chm)[None], t(c3)[None],
                                     t(cam)[None], t(intr)[None], t(dist)[None])
-            out["v2v"] = v if v.size <= 200_000 else v.reshape(-1)[::4].copy()
-            out["v2v_stride"] = 1 if v.size <= 200_000 else 4
+            vs = 1 if v.size <= 200_000 else (4 if v.size <= 1_200_000 else 16)
+            out["v2v"] = v if vs == 1 else v.reshape(-1)[::vs].copy()
+            out["v2v_stride"] = vs
             out["points3D"] = p3[0].numpy()
             out["confidences"] = conf[0].numpy()
             out["kps_true"] = kps.astype(np.float32)
@@ -210,13 +215,22 @@ def main():
         ("tiny_clamp", T, 2, 3, S.make_v2v_weights(T.K, 0, "he"), dict(chm_shift=[[40, -25]] * T.ncam)),
         ("tiny_sp15", S.Shape3D(ncam=3, K=4, bbox=64, roi=36, spacing=1.5), 4, 4,
          S.make_v2v_weights(4, 3, "he"), dict()),
+        ("tiny_fc", S.Shape3D(ncam=3, K=4, bbox=64, roi=36, spacing=1.5), 4, 6,
+         S.make_v2v_weights(4, 3, "he"), dict(float_centre="half")),
         ("small_mh", SM, 5, 5, mh, dict(full=False, sample=4, idx_full=True)),
         ("example_mh", EX, 0, 0, mh, dict(full=False)),
         ("example_he", EX, 1, 1, S.make_v2v_weights(EX.K, 4, "he"), dict(full=False)),
-        ("micro_idx", S.MICRO, 0, 0, None, dict(full=False, with_v2v=False, sample=128)),
-        ("stress_idx", S.STRESS, 0, 0, None, dict(full=False, with_v2v=False, sample=256)),
+        # BASELINE configs 2 and 5 end to end (V2V at h=32/q=16 and h=48/q=24): MonkeyHand weights on the micro shape,
+        # seeded "he" weights on the stress shape
+        ("micro_idx", S.MICRO, 0, 0, mh, dict(full=False, sample=128)),
+        ("stress_idx", S.STRESS, 0, 0, S.make_v2v_weights(S.STRESS.K, 6, "he"), dict(full=False, sample=256)),
     ]
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only and os.path.exists(os.path.join(HERE, "MANIFEST.json")):
+        manifest = json.load(open(os.path.join(HERE, "MANIFEST.json")))
     for name, sh, rs, fs, w, kw in cases:
+        if only and name not in only:
+            continue
         if w is None:
             w = S.make_v2v_weights(sh.K, 0, "ref")
         o = run_case(name, sh, rs, fs, w, **kw)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ALL_CASES, V2V_CASES, case_weights, load_case, sha
+from conftest import ALL_CASES, V2V_CASES, case_weights, decisive_argmax, load_case, oracle_forward, sha
 from test_host import cfg_of
 
 pytestmark = pytest.mark.gpu
@@ -223,7 +223,7 @@ def test_v2v_fp32(oracle, name):
     vol, _ = oracle.repro_layer_forward(oracle.pad_heatmaps(x["hm"]), x["c3"], x["chm"], x["cam"], x["intr"],
                                         x["dist"], sh.G, sh.spacing)
     xin = (vol / np.float32(255.0))[None]
-    want = oracle.v2v_forward(w, xin).numpy()
+    want = oracle_forward(name)["v2v"][None]
     net = V2VNet(sh.K, sh.K, precision="fp32")
     net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
     net = net.to(DEV)
@@ -240,8 +240,7 @@ def test_v2v_fp32(oracle, name):
 def test_tail(oracle, name):
     from jarvis_hybridnet_b200 import centroid_tail
     sh, x, g = load_case(name)
-    out = oracle.hybrid3d_forward(case_weights(name, sh.K), x["hm"], x["c3"], x["chm"], x["cam"], x["intr"],
-                                  x["dist"], sh.roi, sh.spacing)
+    out = oracle_forward(name)
     pts, conf, am = centroid_tail(dev(out["v2v"])[None], sh.spacing, sh.roi, dev(x["c3"])[None], want_argmax=True)
     assert np.array_equal(am[0].cpu().numpy(), out["argmax"])                  # bit-exact argmax voxel
     assert np.abs(pts[0].cpu().numpy() - out["points"]).max() < 0.05           # mm
@@ -257,7 +256,10 @@ def test_hybrid3d_fp32_end_to_end(oracle, name):
     pts, conf, am = net(*repro_inputs(x))
     assert np.abs(pts[0].cpu().numpy() - g["points3D"]).max() < 0.05           # mm, fp32 bar
     np.testing.assert_allclose(conf[0].cpu().numpy(), g["confidences"], rtol=1e-4, atol=1e-5)
-    assert (am[0].cpu().numpy() == g["argmax"]).mean() >= 0.9                  # ties under fp32 reassociation aside
+    # argmax voxel: bit-exact wherever the maximum is decisive (top-2 gap above fp32 re-association noise of the network)
+    dec = decisive_argmax(oracle_forward(name)["v2v"])
+    assert dec.mean() >= 0.5, "fixture has too few decisive maxima to test the argmax"
+    assert np.array_equal(am[0].cpu().numpy()[dec], g["argmax"][dec])
 
 
 def test_accelerate_seam():

@@ -9,7 +9,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import ROOT, V2V_CASES, case_weights, load_case
+from conftest import ROOT, V2V_CASES, case_weights, decisive_argmax, load_case, oracle_forward
 from test_gpu_parity import dev, repro_inputs
 
 pytestmark = pytest.mark.gpu
@@ -27,7 +27,9 @@ def make_net(K, weights, precision="bf16"):
     return net.to(DEV)
 
 
-LAYER_CASES = [(K, h, B) for K, h, B in [(23, 12, 1), (5, 12, 2), (23, 36, 1), (23, 20, 3)]]
+# (23, 32, 1) and (23, 48, 1): the layer shapes of BASELINE configs 2 and 5 (h = 32 / q = 16 and h = 48 / q = 24, where the
+# stacked 3x3x3 kernel drops to a 4-slot plane ring)
+LAYER_CASES = [(K, h, B) for K, h, B in [(23, 12, 1), (5, 12, 2), (23, 36, 1), (23, 20, 3), (23, 32, 1), (23, 48, 1)]]
 
 
 @pytest.mark.parametrize("K,h,B", LAYER_CASES)
@@ -85,10 +87,13 @@ def test_forward_host_pipelined_equals_forward():
     for chunk in (2, 5, 1, 2):
         res, h2d, d2h = net.forward_host(host, chunk=chunk)
         assert h2d == sum(t.numel() * t.element_size() for t in host) and d2h == want.numel() * 4
-        # InstanceNorm statistics are accumulated with atomics, so runs agree to bf16 rounding noise (a tenth of the 0.5 mm bf16 bar), not bit for bit
-        assert torch.allclose(res, want, rtol=0, atol=5e-2), (chunk, (res - want).abs().max())
+        # the InstanceNorm statistics are per-CTA partial sums added in a fixed order (deterministic), but how a sample's
+        # tiles fall into CTA ranges depends on the frame sets per call: fp32 re-association noise, far below bf16 rounding
+        assert torch.allclose(res, want, rtol=0, atol=5e-3), (chunk, (res - want).abs().max())
+        if chunk == 5:
+            assert torch.equal(res, want)                            # same partition -> same bits
     pts2, conf2, _ = net(*devt)
-    assert torch.allclose(pts2, pts, rtol=0, atol=5e-2) and torch.allclose(conf2, conf, rtol=0, atol=1e-3)
+    assert torch.equal(pts2, pts) and torch.equal(conf2, conf)      # run to run: bit-identical
 
 
 @pytest.mark.parametrize("name", V2V_CASES)
@@ -98,7 +103,7 @@ def test_v2v_bf16_vs_oracle(oracle, name):
     vol, _ = oracle.repro_layer_forward(oracle.pad_heatmaps(x["hm"]), x["c3"], x["chm"], x["cam"], x["intr"], x["dist"],
                                         sh.G, sh.spacing)
     xin = (vol / np.float32(255.0))[None]
-    want = oracle.v2v_forward(w, xin).numpy()
+    want = oracle_forward(name)["v2v"][None]
     got = make_net(sh.K, w)(dev(xin)).cpu().numpy()
     scale = np.abs(want).max()
     err = np.abs(got - want)
@@ -139,7 +144,7 @@ def test_bf16_batch_matches_single(oracle):
     pts, conf, _ = net(*args)
     for b in range(3):
         p1, c1, _ = net(*[a[b:b + 1] for a in args])
-        assert (p1[0] - pts[b]).abs().max().item() < 2e-2              # atomics reorder the fp32 statistics sums
+        assert (p1[0] - pts[b]).abs().max().item() < 5e-3              # only the CTA partition of the statistics differs
         want = oracle.hybrid3d_forward(w, sets[b][0], sets[b][1], sets[b][2], cam, intr, dist, sh.roi, sh.spacing)
         assert np.abs(pts[b].cpu().numpy() - want["points"]).max() < 0.5
 
@@ -159,6 +164,113 @@ def test_forward_graph_replay_equals_forward():
         want = [t.clone() for t in net(*args)]
         got = net.forward_graph(*args)
         torch.cuda.synchronize()
-        assert torch.allclose(got[0], want[0], rtol=0, atol=5e-2), (seed, (got[0] - want[0]).abs().max())
-        assert torch.allclose(got[1], want[1], rtol=0, atol=1e-3)
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], want[2]), seed
     assert len(net._graphs) == 1
+
+
+@pytest.mark.parametrize("K,h,B", [(23, 36, 2), (23, 12, 1), (5, 20, 3), (23, 48, 1)])
+def test_fused_head_argmax_is_exact(K, h, B):
+    """The fused output layer + centroid epilogue (head_tc.cu) against torch's fp32 1x1x1 convolution of the SAME bf16
+    activations and weights: argmax voxel bit-exact wherever the maximum is decisive, centroid / confidence to fp32 noise."""
+    import jarvis_hybridnet_b200.synth as S
+    from jarvis_hybridnet_b200 import _lib
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    w = S.make_v2v_weights(K, 3, "he")
+    net = make_net(K, w)
+    g = torch.Generator(device="cpu").manual_seed(7 + h)
+    x = torch.randn((B, 2 * K, h, h, h), generator=g) * 3.0
+    for b in range(B):                                   # one sharp peak per key point on top of the noise, like a real volume
+        for k in range(2 * K):
+            i, j, l = [int(v) for v in torch.randint(0, h, (3,), generator=g)]
+            x[b, k, i, j, l] += 40.0
+    x = bf16_round(x).to(DEV)
+    wt = bf16_round(torch.as_tensor(w["output_layer.weight"])).to(DEV)
+    bs = torch.as_tensor(w["output_layer.bias"]).to(DEV)
+    v = F.conv3d(x, wt, bs)                              # [B,K,h,h,h] fp32
+    c3 = torch.tensor([[10.5, -20.0, 30.25]] * B, device=DEV)
+    spacing, roi = 2.0, 4.0 * h
+    lib = _lib.load()
+    need = _lib.c_size_t()
+    _lib.check(lib.jhn_v2v_debug_layer_workspace_bytes(net._get_handle(), 11, B, h, need))
+    ws = torch.empty(need.value, dtype=torch.uint8, device=DEV)
+    pts = torch.empty((B, K, 3), device=DEV); conf = torch.empty((B, K), device=DEV)
+    am = torch.empty((B, K), dtype=torch.int32, device=DEV)
+    _lib.check(lib.jhn_v2v_debug_head_centroid(net._get_handle(), _lib.dptr(x), B, h, spacing, roi, _lib.dptr(c3), _lib.dptr(pts),
+                                               _lib.dptr(conf), _lib.dptr(am), _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
+    vf = v.reshape(B, K, -1)
+    want_am = vf.argmax(2).cpu().numpy()
+    dec = np.stack([decisive_argmax(vf[b].cpu().numpy(), rel=1e-5) for b in range(B)])
+    assert dec.mean() > 0.8
+    assert np.array_equal(am.cpu().numpy()[dec], want_am[dec])
+    hf = F.softplus(v.double())
+    n = hf.sum((2, 3, 4))
+    ar = torch.arange(h, device=DEV, dtype=torch.float64)
+    cx = (hf * ar[:, None, None]).sum((2, 3, 4)) / n
+    cy = (hf * ar[None, :, None]).sum((2, 3, 4)) / n
+    cz = (hf * ar[None, None, :]).sum((2, 3, 4)) / n
+    want = torch.stack([cx, cy, cz], 2) * spacing * 2 - roi / 2 + c3[:, None, :].double()
+    assert (pts.double() - want).abs().max().item() < 2e-3           # mm
+    want_conf = hf.reshape(B, K, -1).max(2)[0].clamp(max=255.0) / 255.0
+    assert torch.allclose(conf.double(), want_conf, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["example_mh", "micro_idx", "tiny_fc"])
+def test_bf16_argmax_decisive_key_points(name):
+    """End to end in bf16 the activations differ from fp32 by rounding, so only the clearly decisive maxima (top-2 gap
+    above 5 % of the volume's scale) are required to land on the reference's argmax voxel."""
+    from jarvis_hybridnet_b200 import HybridNet3D
+    sh, x, g = load_case(name)
+    net = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, case_weights(name, sh.K), precision="bf16").to(DEV)
+    _, _, am = net(*repro_inputs(x))
+    dec = decisive_argmax(oracle_forward(name)["v2v"], rel=5e-2)
+    assert np.array_equal(am[0].cpu().numpy()[dec], g["argmax"][dec]), (dec.sum(), am[0].cpu().numpy(), g["argmax"])
+
+
+@pytest.mark.parametrize("name", ["tiny_s0", "small_mh", "example_mh"])
+def test_heatmap_formats_agree(name):
+    """jhn_hybrid3d_forward fed fp32 planar maps (the reference's tensor), the gather-native fp16 channels-last form
+    (jhn_heatmap_convert) and bf16 channels-last: the fp16 form is the internal staging copy itself -> identical bits;
+    bf16 input loses 3 mantissa bits before the gather -> bf16 bar."""
+    from jarvis_hybridnet_b200 import HybridNet3D, _lib
+    sh, x, g = load_case(name)
+    net = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, case_weights(name, sh.K), precision="bf16").to(DEV)
+    args = repro_inputs(x)
+    ref = [t.clone() for t in net(*args)]
+    cl16 = _lib.heatmap_convert(args[0], sh.hs, _lib.HM_F16_CL)
+    assert cl16.dtype == torch.float16 and tuple(cl16.shape) == (1, sh.ncam, sh.hs, sh.hs, 24)
+    # known answer of the conversion: interior pixel (y, x) of camera c holds hm[c, :, y-1, x-1] / 16, the border is zero
+    want = torch.zeros_like(cl16, dtype=torch.float32)
+    want[0, :, 1:-1, 1:-1, :sh.K] = args[0][0].permute(0, 2, 3, 1) * _lib.HM_F16_SCALE
+    assert torch.equal(cl16.float(), want.half().float())
+    got = net(cl16, *args[1:])
+    assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    clb = _lib.heatmap_convert(args[0], sh.hs, _lib.HM_BF16_CL)
+    gotb = net(clb, *args[1:])
+    assert (gotb[0] - ref[0]).abs().max().item() < 0.25 and np.abs(gotb[0][0].cpu().numpy() - g["points3D"]).max() < 0.5
+
+
+def test_sub_batch_invariance():
+    """jhn_hybrid3d_forward walks a batch in passes (L2-resident activations); frame sets are independent, so the pass
+    size must not matter beyond the CTA partition of the statistics sums."""
+    import jarvis_hybridnet_b200.synth as S
+    from jarvis_hybridnet_b200 import HybridNet3D, _lib
+    sh = S.SMALL
+    cam, intr, dist = S.make_rig(sh.ncam, 2)
+    sets = [S.make_frameset(sh, cam, intr, dist, s) for s in range(7)]
+    net = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, S.make_v2v_weights(sh.K, 2, "he"), precision="bf16").to(DEV)
+    stack = lambda i: torch.stack([dev(s[i]) for s in sets])
+    rep = lambda a: dev(a)[None].expand(7, *a.shape).contiguous()
+    args = (stack(0), stack(1), stack(2), rep(cam), rep(intr), rep(dist))
+    try:
+        outs = {}
+        for sb in (7, 3, 2, 1):
+            assert _lib.set_sub_batch(sb) == sb
+            outs[sb] = [t.clone() for t in net(*args)]
+        for sb in (3, 2, 1):
+            assert (outs[sb][0] - outs[7][0]).abs().max().item() < 5e-3, sb
+            assert torch.allclose(outs[sb][1], outs[7][1], rtol=0, atol=1e-4)
+        one = [net(*[a[b:b + 1] for a in args])[0] for b in range(7)]
+        assert torch.equal(torch.cat(one), outs[1][0])              # pass size 1 == seven B=1 calls, bit for bit
+    finally:
+        _lib.set_sub_batch(0)

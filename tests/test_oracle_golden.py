@@ -5,7 +5,7 @@ output / key points within fp32 re-association noise of the reference's own CPU 
 import numpy as np
 import pytest
 
-from conftest import ALL_CASES, V2V_CASES, case_weights, load_case, sha
+from conftest import ALL_CASES, V2V_CASES, case_weights, load_case, oracle_forward, sha
 
 
 @pytest.mark.parametrize("name", ALL_CASES)
@@ -39,8 +39,7 @@ def test_volume(oracle, name):
 @pytest.mark.parametrize("name", V2V_CASES)
 def test_v2v_and_tail(oracle, name):
     sh, x, g = load_case(name)
-    out = oracle.hybrid3d_forward(case_weights(name, sh.K), x["hm"], x["c3"], x["chm"], x["cam"], x["intr"],
-                                  x["dist"], sh.roi, sh.spacing)
+    out = oracle_forward(name)
     v = out["v2v"].reshape(-1)[::int(g["v2v_stride"])].reshape(g["v2v"].shape)
     scale = np.abs(g["v2v"]).max()
     assert np.abs(v - g["v2v"]).max() <= 2e-5 * scale + 1e-6
