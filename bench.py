@@ -309,6 +309,143 @@ def run_glue(args, wl):
     emit(line)
 
 
+def torch_reference_gpu(sh, weights, batch, n_frame_sets=8, reps=3):
+    """"The kernel to beat" (SURVEY.md section 8d): the reference's own algorithm for stages a2-a10 with the SAME torch
+    operators in the same order on the B200 — cuBLAS SGEMM + ATen upsample_trilinear3d + index_select + mean
+    (jarvis/hybridnet/repro_layer.py:40-119), cuDNN conv3d / conv_transpose3d + ATen instance_norm
+    (jarvis/hybridnet/v2vnet.py:12-102), the softplus centroid (jarvis/hybridnet/model.py:65-88) — one frame set per
+    call like the reference (repro_layer.py:112-117), inputs resident.  A baseline leg only: library kernels, nothing of
+    this repo's product path; /root/reference itself does not exist on the GPU box, so the modules cannot be imported."""
+    import torch
+    import torch.nn.functional as F
+    dev = torch.device("cuda")
+    hm_b, c3_b, chm_b, cam_b, intr_b, dist_b = batch
+    G, h, hs, K, ncam = sh.G, sh.h, sh.hs, sh.K, sh.ncam
+    W = {k: torch.as_tensor(v).to(dev) for k, v in weights.items()}
+    half = G // 2 // 2
+    ar = torch.arange(h, dtype=torch.float32, device=dev) - half
+    grid0 = torch.stack(torch.meshgrid(ar, ar, ar, indexing="ij"), dim=3) * sh.spacing * 2          # repro_layer.py:26-36
+    xx, yy, zz = torch.meshgrid(torch.arange(h, device=dev), torch.arange(h, device=dev), torch.arange(h, device=dev), indexing="ij")
+
+    def conv(p, t, stride=1, pad=0):
+        return F.conv3d(t, W[p + ".weight"], W[p + ".bias"], stride=stride, padding=pad)
+
+    def basic(p, t, k, stride):
+        return F.relu(F.instance_norm(conv(p + ".block.0", t, stride, (k - 1) // 2)))
+
+    def res(p, t):
+        r = F.relu(F.instance_norm(conv(p + ".res_branch.0", t, 1, 1)))
+        return F.relu(F.instance_norm(conv(p + ".res_branch.3", r, 1, 1)) + t)
+
+    def one(hm, c3, chm, cam, intr, dist):
+        hp = F.pad(hm, [1, 1, 1, 1])                                                                # model.py:65-66
+        x = grid0 + c3                                                                              # repro_layer.py:113
+        intr_p, dist_p, chm_p = intr.permute(1, 2, 0), dist.permute(1, 2, 0), chm.permute(1, 0)
+        x = torch.cat((x, torch.ones(h, h, h, 1, device=dev)), 3)
+        pa = torch.matmul(x.view(1, -1, 4), cam).view(-1, h, h, h, 3).permute(1, 2, 3, 4, 0)
+        v1 = pa[:, :, :, 0] / pa[:, :, :, 2] - intr_p[2, 0]
+        v2 = pa[:, :, :, 1] / pa[:, :, :, 2] - intr_p[2, 1]
+        r2 = torch.square(v1 / intr_p[0, 0]) + torch.square(v2 / intr_p[1, 1])
+        d = 1 + (dist_p[0, 0] + dist_p[0, 1] * r2) * r2
+        v1 = v1 * d + intr_p[2, 0]
+        v2 = v2 * d + intr_p[2, 1]
+        v1 = torch.clamp(v1, chm_p[0] - (hs - 1), chm_p[0] + hs - 2) - chm_p[0] + hs - 1
+        v2 = torch.clamp(v2, chm_p[1] - (hs - 1), chm_p[1] + hs - 2) - chm_p[1] + hs - 1
+        up = lambda v: F.interpolate(v.permute(3, 0, 1, 2).reshape(1, ncam, h, h, h), size=(G, G, G),
+                                     mode="trilinear").view(ncam, G, G, G).permute(1, 2, 3, 0)
+        f1, f2 = up(v1), up(v2)
+        rp = ((f2 / 2).int() * hs + (f1 / 2).int()).permute(3, 0, 1, 2).long()                      # :82-83
+        off = torch.arange(0, hs * hs * ncam, hs * hs, device=dev)
+        hmf = hp.transpose(0, 1).flatten(1)                                                         # [K, ncam*hs*hs]  :97-103
+        rp = (rp.flatten(1).transpose(1, 0) + off).transpose(1, 0).flatten()
+        vol = torch.mean(torch.index_select(hmf, 1, rp).view(K, ncam, G, G, G), dim=1)[None]
+        x = basic("front_layers.0", vol / 255., 3, 2)                                               # v2vnet.py:98-102
+        x = res("front_layers.1", x)
+        s = res("encoder_decoder.skip_res1", x)
+        y = basic("encoder_decoder.encoder_pool1", x, 2, 2)
+        y = res("encoder_decoder.mid_res", y)
+        p = "encoder_decoder.decoder_upsample1.block.0"
+        y = F.relu(F.instance_norm(F.conv_transpose3d(y, W[p + ".weight"], W[p + ".bias"], stride=2)))
+        y = res("encoder_decoder.decoder_res1", y) + s
+        hf = F.softplus(conv("output_layer", y))                                                    # model.py:72-73
+        n = torch.sum(hf, dim=[2, 3, 4])
+        px = torch.sum(hf * xx, dim=[2, 3, 4]) / n
+        py = torch.sum(hf * yy, dim=[2, 3, 4]) / n
+        pz = torch.sum(hf * zz, dim=[2, 3, 4]) / n
+        pts = torch.stack([px, py, pz], dim=2) * sh.spacing * 2 - sh.roi / 2. + c3
+        conf = torch.clamp(torch.max(hf.view(1, K, -1), dim=2)[0], max=255.) / 255.
+        return pts, conf
+
+    out = {}
+    n = min(n_frame_sets, hm_b.shape[0])
+    for tag, tf32 in (("tf32_on", True), ("tf32_off", False)):
+        torch.backends.cudnn.allow_tf32 = tf32                      # the reference runs with torch's default (conv TF32 on)
+        with torch.no_grad():
+            for b in range(2):
+                one(hm_b[b], c3_b[b], chm_b[b], cam_b[b], intr_b[b], dist_b[b])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                for b in range(n):
+                    pts, conf = one(hm_b[b], c3_b[b], chm_b[b], cam_b[b], intr_b[b], dist_b[b])
+            e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * n)
+        out[tag] = dict(ms_per_frame_set=ms, frame_sets_per_sec=1e3 / ms)
+    torch.backends.cudnn.allow_tf32 = True
+    out["note"] = ("reference algorithm restated op for op with torch library kernels (cuBLAS, cuDNN, ATen) on this GPU, one frame "
+                   "set per call as in repro_layer.py:112-117, %d frame sets x %d repetitions, fp32 inputs resident" % (n, reps))
+    return out
+
+
+def micro_reproject_tail(sh, B, pk, steps=10):
+    """BASELINE.json configs[1] / metric (ii): ReprojectionLayer (+ /255) and the centroid tail on their own, fp32 and bf16,
+    as achieved HBM GB/s over the algorithmic bytes of SURVEY.md section 8d."""
+    import torch
+    from types import SimpleNamespace as NS
+    from jarvis_hybridnet_b200 import ReprojectionLayer, centroid_tail
+    cfg = NS(HYBRIDNET=NS(GRID_SPACING=sh.spacing, ROI_CUBE_SIZE=sh.roi, NUM_CAMERAS=sh.ncam),
+             KEYPOINTDETECT=NS(BOUNDING_BOX_SIZE=sh.bbox, NUM_JOINTS=sh.K))
+    batches, _, _ = make_inputs(sh, B, 2, seed=5, distinct=4)
+    devb = [[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in b] for b in batches]
+    out = {}
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for prec, s_in, s_out in (("fp32", 4, 4), ("bf16", 4, 2)):
+        L = ReprojectionLayer(cfg, precision=prec)
+        layout = "ncdhw" if prec == "fp32" else "v2v"
+        ms = timed(lambda i: L.forward_batched(*devb[i % 2], post_divide=255.0, volume_layout=layout))
+        by = B * repro_bytes(sh, s_in, s_out)
+        out["reproject_" + prec] = dict(ms_per_step=ms, algorithmic_bytes_per_step=by, GB_per_s=by / (ms * 1e-3) / 1e9,
+                                        frac_of_hbm=by / (ms * 1e-3) / 1e9 / pk["hbm"], input="fp32 planar (reference tensor)",
+                                        volume="fp32 NCDHW" if prec == "fp32" else "bf16 V2V layout")
+    # gather-native fp16 channels-last input (row f2 layout): no staging pass, 2 bytes per input element
+    L = ReprojectionLayer(cfg, precision="bf16")
+    cl = [torch.from_numpy(S.to_cl16(b[0])).cuda() for b in batches]
+    ms = timed(lambda i: L.forward_batched(cl[i % 2], *devb[i % 2][1:], post_divide=255.0, volume_layout="v2v"))
+    by = B * repro_bytes(sh, 2, 2)
+    out["reproject_bf16_f16cl_input"] = dict(ms_per_step=ms, algorithmic_bytes_per_step=by, GB_per_s=by / (ms * 1e-3) / 1e9,
+                                             frac_of_hbm=by / (ms * 1e-3) / 1e9 / pk["hbm"], input="fp16 channels-last", volume="bf16 V2V layout")
+    v = [torch.randn((B, sh.K, sh.h, sh.h, sh.h), device="cuda") * 20 for _ in range(max(2, int(600e6 // (B * sh.K * sh.h ** 3 * 4)) + 1))]
+    ms = timed(lambda i: centroid_tail(v[i % len(v)], sh.spacing, sh.roi, devb[0][1]))
+    by = B * sh.K * sh.h ** 3 * 4
+    out["tail_fp32"] = dict(ms_per_step=ms, algorithmic_bytes_per_step=by, GB_per_s=by / (ms * 1e-3) / 1e9,
+                            frac_of_hbm=by / (ms * 1e-3) / 1e9 / pk["hbm"],
+                            note="stand-alone fp32 tail; on the bf16 path the tail is the output layer's epilogue (zero extra traffic)")
+    out["config"] = dict(ncam=sh.ncam, K=sh.K, heatmap=sh.hm, grid=sh.G, frame_sets_per_step=B, l2="two input batches alternate")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,6 +460,7 @@ def main():
     ap.add_argument("--job-frame-sets", type=int, default=0,
                     help="also run one sharded job of this many frame sets with a single gather at the end (BASELINE configs[3]: 100000)")
     ap.add_argument("--no-latency", action="store_true", help="skip the B=1 eager / CUDA-graph latency measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the torch GPU baseline and the configs 2 / 5 side measurements")
     ap.add_argument("--sub-batch", type=int, default=0, help="frame sets per internal pass of jhn_hybrid3d_forward (0 = library default)")
     args = ap.parse_args()
     claim_stdout()
@@ -357,13 +495,7 @@ def main():
     precision = args.precision
     weights = S.make_v2v_weights(sh.K, 0, "he")
     if precision == "auto":
-        try:
-            probe = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, weights, precision="bf16").cuda()
-            probe.v2vNet._get_handle()
-            precision = "bf16"
-            del probe
-        except RuntimeError:
-            precision = "fp32"
+        precision = "bf16"          # BASELINE.json configs[2] names bf16; a failure to build the tensor-core handle is an error, not a downgrade
     net = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, weights, precision=precision).cuda()
 
     n_pool = 2
@@ -398,13 +530,38 @@ def main():
     ms = float(t.item())
     value = world * B * K_steps / (ms * 1e-3)
 
-    # ---- end to end through the public API with host buffers -------------------------------------
+    # ---- the same with the heat maps resident in the gather-native layout (fp16 channels-last, SURVEY.md section 8 row f2:
+    # what a 2D head that writes for the gather emits; jhn_heatmap_convert / jhn_efftrack_head produce it on the device) ----
+    value_cl = None
+    if precision == "bf16":
+        host_cl = [[to_t(S.to_cl16(b[0])).pin_memory()] + h[1:] for b, h in zip(batches, host)]
+        dev_cl = [[h[0].cuda(non_blocking=True)] + d[1:] for h, d in zip(host_cl, devb)]
+        for i in range(min(W, 3)):
+            net(*dev_cl[i % n_pool])
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(K_steps):
+            net(*dev_cl[i % n_pool])
+        c1.record()
+        barrier()
+        t = torch.tensor([c0.elapsed_time(c1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        value_cl = dict(value=world * B * K_steps / (float(t.item()) * 1e-3), unit="frame-sets/s", ms_per_step=float(t.item()) / K_steps,
+                        input="heat maps resident as fp16 channels-last [B,ncam,hs,hs,24] (JHN_HM_F16_CL): no staging pass")
+    else:
+        host_cl = host
+
+    # ---- end to end through the public API with host buffers: pinned host tensors in, [B,K,4] back in pinned memory.
+    # On the bf16 path the heat maps cross PCIe in the gather-native fp16 channels-last form (9.7 MB instead of 18.1 MB per
+    # frame set at the Example shape); everything else is the reference's fp32 / int32 tensors. --------------------------
     for i in range(min(W, 2)):
-        net.forward_host(host[i % n_pool])
+        net.forward_host(host_cl[i % n_pool])
     barrier()
     t0 = time.perf_counter()
     for i in range(K_steps):
-        res, h2d, d2h = net.forward_host(host[i % n_pool])
+        res, h2d, d2h = net.forward_host(host_cl[i % n_pool])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device="cuda")
@@ -413,7 +570,8 @@ def main():
     e2e_s = float(t.item())
     clocks = clk.stop()
     e2e = dict(value=world * B * K_steps / e2e_s, unit="frame-sets/s", h2d_bytes_per_step=int(h2d),
-               d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * e2e_s / K_steps)
+               d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * e2e_s / K_steps,
+               heatmap_format="fp16 channels-last (JHN_HM_F16_CL)" if precision == "bf16" else "fp32 planar")
 
     # ---- B=1 latency (the reference's predictor runs one frame set per call): eager launches vs CUDA-graph replay ----
     latency = None
@@ -527,6 +685,32 @@ def main():
     top = next(iter(kern)) if kern else None                                # dominant kernel = most device time per step
     roofline = rooflines.get(top)
 
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extras and args.workload == "c3_full3d_example":
+        extra = dict(torch_gpu_baseline=torch_reference_gpu(sh, weights, devb[0]),
+                     c2_micro=micro_reproject_tail(S.MICRO, WORKLOADS["c2_micro"]["batch"], pk))
+        try:                                                        # BASELINE.json configs[4]: 16 cameras, 96^3 grid, bf16 (this GPU's share)
+            st = S.STRESS
+            Bs = WORKLOADS["c5_stress"]["batch"]
+            bs, _, _ = make_inputs(st, Bs, 2, seed=3, distinct=2)
+            nets = HybridNet3D(st.K, st.bbox, st.roi, st.spacing, S.make_v2v_weights(st.K, 0, "he"), precision=precision).cuda()
+            dbs = [[to_t(a).cuda() for a in b] for b in bs]
+            for i in range(3):
+                nets(*dbs[i % 2])
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(6):
+                nets(*dbs[i % 2])
+            s1.record(); torch.cuda.synchronize()
+            msx = s0.elapsed_time(s1) / 6
+            extra["c5_stress"] = dict(frame_sets_per_sec=Bs / (msx * 1e-3), ms_per_step=msx,
+                                      config=dict(ncam=st.ncam, K=st.K, heatmap=st.hm, grid=st.G, frame_sets_per_step=Bs, dtype=precision),
+                                      v2v_algorithmic_TFLOP_per_step=Bs * v2v_flops(st)["total"] / 1e12,
+                                      note="one GPU's share of BASELINE.json configs[4]; `bench.py --gpus 8 --workload c5_stress` is the 8-GPU run")
+            del nets, dbs
+        except RuntimeError as e:
+            extra["c5_stress"] = dict(error=str(e)[:200])
     if rank == 0:
         cb = None if args.no_cpu_baseline or world > 1 else cpu_baseline(sh)
         line = dict(metric="frame_sets_per_sec", value=value, unit="frame-sets/s", n_gpus=world, steps=K_steps, warmup=W,
@@ -539,7 +723,8 @@ def main():
                                 timed_region="heat maps -> key points (stages a2-a10); 2D CNN, decode, CSV excluded",
                                 roi_share_of_heatmap=roi),
                     clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cb,
-                    stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms, latency_b1=latency, job=job)
+                    stages=stages, kernels=kern, rooflines=rooflines, gather_ms=gather_ms, latency_b1=latency, job=job,
+                    value_f16cl_input=value_cl, extra=extra)
         emit(line)
     if world > 1:
         dist.barrier()

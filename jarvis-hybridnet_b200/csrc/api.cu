@@ -61,7 +61,7 @@ int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st);
 void tc_destroy(jhn_v2v *net);
 size_t tc_workspace(const jhn_v2v *net, int B, int G);
 int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws,
-               size_t ws_bytes, cudaStream_t st, const TailArgs *tail, int carveB);
+               size_t ws_bytes, cudaStream_t st, const TailArgs *tail, int carveB, int borders);
 int tc_debug_head(const jhn_v2v *net, const float *in, int B, int h, const TailArgs &tail, void *ws, size_t ws_bytes, cudaStream_t st);
 bool head_supported(int K, int cin_pad, int cout_pad, int D);
 
@@ -89,14 +89,15 @@ unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_o
 void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 int jhn_debug_set_gather_box_bytes(int bytes) { return gather_set_box_bytes(bytes); }
 
-// Frame sets per internal pass of jhn_hybrid3d_forward.  Default 8: at the Example shape one pass then keeps a
-// convolution's input + output (2 x 42 MB) inside the 126 MB L2, so the normalisation passes and the next layer's
-// operand stream hit L2 instead of HBM (measured: profiles/r02_*subbatch*).  Frame sets are independent, so the
-// result does not depend on the value.
-static std::atomic<int> g_sub_batch{8};
+// Frame sets per internal pass of jhn_hybrid3d_forward.  Default: the whole batch in one pass.  Passes of 8 keep a
+// convolution's input + output (2 x 42 MB at the Example shape) inside the 126 MB L2, but measured on the B200 that buys
+// nothing (profiles/r02_run1_subbatch.txt: 32 -> 3.36 ms, 16 -> 3.58, 8 -> 4.02, 4 -> 4.91 ms per 32 frame sets): the
+// persistent kernels lose more to their shorter tile ranges than the normalisation passes gain.  The knob stays for
+// callers that must bound the workspace.  Frame sets are independent, so results do not depend on it.
+static std::atomic<int> g_sub_batch{1 << 20};
 int jhn_set_sub_batch(int n)
 {
-    if (n <= 0) n = 8;
+    if (n <= 0) n = 1 << 20;
     g_sub_batch.store(n, std::memory_order_relaxed);
     return n;
 }
@@ -235,7 +236,7 @@ int jhn_v2v_forward(const jhn_v2v *net, const void *volume_in, int in_layout, in
         if (in_layout != JHN_VOL_NCDHW_F32) return fail(JHN_ERR_ARG, "fp32 V2V takes the NCDHW fp32 volume");
         return v2v_f32_forward(net, (const float *)volume_in, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream);
     }
-    return tc_forward(net, volume_in, in_layout, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0);
+    return tc_forward(net, volume_in, in_layout, B, G, out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0, -1);
 }
 
 int jhn_v2v_debug_layer_workspace_bytes(const jhn_v2v *net, int layer, int B, int D, size_t *bytes)
@@ -327,6 +328,8 @@ int jhn_hybrid3d_forward(const jhn_v2v *net, const void *heatmaps, int hm_format
                                                             : (size_t)ncam * hs * hs * KP * 2;       // bytes per frame set
     const int c2 = (2 * K + 15) / 16 * 16, c1 = (K + 15) / 16 * 16;
     const bool fused_head = net->precision == JHN_BF16 && head_supported(K, c2, c1, h);
+    // zero borders of every padded tensor in the workspace: intact iff this workspace was last carved the same way
+    const int borders = net->precision == JHN_BF16 && net->borders_cached(workspace, jhn_v2v::border_sig(0, SB, G, ncam, hs)) ? 1 : 0;
     for (int b0 = 0; b0 < B; b0 += SB) {
         const int nb = B - b0 < SB ? B - b0 : SB;
         const size_t bc = (size_t)b0 * ncam;
@@ -335,17 +338,22 @@ int jhn_hybrid3d_forward(const jhn_v2v *net, const void *heatmaps, int hm_format
                          nb, ncam, K, hs, G, spacing, lerp_mode, 255.f, net->precision, hybrid_layout(net), vol, nullptr, 0};
         // per-sample offsets of the padded layouts do not depend on the batch size, and the first pass always has nb == SB:
         // a shorter last pass finds the borders of its samples already zero
-        if (net->precision == JHN_BF16) ra.borders_valid = net->borders_cached(vol, SB, G, 16) ? 1 : 0;
+        ra.borders_valid = (borders || b0 > 0) ? 1 : 0;
         JHN_TRY(reproject_launch(ra, ws_r, rws, (cudaStream_t)stream));
         float *pts = points + (size_t)b0 * K * 3, *cf = conf + (size_t)b0 * K;
         int32_t *am = argmax ? argmax + (size_t)b0 * K : nullptr;
         if (fused_head) {
             // bf16 path: the output layer's epilogue is the centroid tail; the [B,K,h^3] volume is never materialised
             TailArgs tail{spacing, roi, center3D + (size_t)b0 * 3, pts, cf, am, vout};
-            JHN_TRY(tc_forward(net, vol, hybrid_layout(net), nb, G, nullptr, ws_v, align_up(v2v, 256), (cudaStream_t)stream, &tail, SB));
+            JHN_TRY(tc_forward(net, vol, hybrid_layout(net), nb, G, nullptr, ws_v, align_up(v2v, 256), (cudaStream_t)stream, &tail, SB,
+                               (borders || b0 > 0) ? 1 : 0));
             continue;
         }
-        JHN_TRY(jhn_v2v_forward(net, vol, hybrid_layout(net), nb, G, vout, ws_v, align_up(v2v, 256), stream));
+        if (net->precision == JHN_BF16)
+            JHN_TRY(tc_forward(net, vol, hybrid_layout(net), nb, G, vout, ws_v, align_up(v2v, 256), (cudaStream_t)stream, nullptr, SB,
+                               (borders || b0 > 0) ? 1 : 0));
+        else
+            JHN_TRY(jhn_v2v_forward(net, vol, hybrid_layout(net), nb, G, vout, ws_v, align_up(v2v, 256), stream));
         JHN_TRY(jhn_centroid_reduce(vout, nb, K, h, spacing, roi, center3D + (size_t)b0 * 3, pts, cf, am, stream));
     }
     return JHN_OK;

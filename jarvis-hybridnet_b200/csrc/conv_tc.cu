@@ -444,7 +444,7 @@ int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st
 // optionally also writes the parity-split copy the following stride-2 convolution reads.  HBM-bound: one block
 // per (sample, 8-channel chunk, z-plane) walks the plane's contiguous run of padded positions with 16-byte
 // accesses; the 8 (mean, rstd) pairs are computed once per block, pad columns are skipped (they stay zero).
-constexpr int NORM_THREADS = 256, NORM_UNROLL = 3;
+constexpr int NORM_THREADS = 256, NORM_UNROLL = 3, NORM_ZB = 4;      // NORM_ZB z-planes per block: the statistics prologue is paid once per 4 planes
 template <bool HAS_RES, bool HAS_POST, bool HAS_PS>
 __global__ void __launch_bounds__(NORM_THREADS)
 tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__restrict__ residual,
@@ -453,7 +453,7 @@ tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__r
 {
     __shared__ float sc[16];                                          // mean[8], rstd[8]
     __shared__ double red[32][8][2];
-    const int z = blockIdx.x, bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
+    const int bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
     const int Wp = D + 2, PP = Wp * Wp;
     {
         // second stage of the statistics: the producing kernel's per-CTA slots of sample b, added in slot order in fp64
@@ -480,9 +480,11 @@ tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__r
     float mean[8], rstd[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mean[i] = sc[i]; rstd[i] = sc[8 + i]; }
-    const size_t plane = ((size_t)bj * Wp + z + 1) * PP;
     const int p_begin = Wp + 1, p_end = D * Wp + D + 1;               // first / one-past-last interior position
     const int Dh = D / 2, Wh = Dh + 2;
+    const int z_end = min(D, ((int)blockIdx.x + 1) * NORM_ZB);
+    for (int z = blockIdx.x * NORM_ZB; z < z_end; ++z) {
+    const size_t plane = ((size_t)bj * Wp + z + 1) * PP;
     for (int p0 = p_begin + threadIdx.x; p0 < p_end; p0 += NORM_THREADS * NORM_UNROLL) {
         uint4 raw[NORM_UNROLL], rs[NORM_UNROLL], pa[NORM_UNROLL];
         bool ok[NORM_UNROLL];
@@ -526,6 +528,7 @@ tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__r
                 ps_out[po] = res;
             }
         }
+    }
     }
 }
 
@@ -839,7 +842,7 @@ struct TcCtx {
         const TcLayer &T = net->tc->layer[l];
         const int nv = D * D * D, CJ = T.cout_pad / 8, Wp = D + 2;
         const uint32_t magic = (uint32_t)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);   // ceil(2^32 / Wp)
-        const dim3 grid(D, B * CJ);
+        const dim3 grid(cdiv(D, NORM_ZB), B * CJ);
         const float inv = 1.f / (float)nv;
 #define JHN_NORM(R, P, S)                                                                                              \
         JHN_LAUNCH("tc_norm_act_kernel", st,                                                                           \
@@ -865,8 +868,10 @@ int head_centroid_launch(const void *in, const __nv_bfloat16 *w, const float *bi
 // `tail` non-null: the output layer runs fused with the centroid tail and `out` is not written (may be null).
 // `carveB` >= B: the workspace is carved for carveB frame sets (a caller that walks a batch in sub-batches keeps one
 // carving, so the cached zero borders stay valid for a shorter last pass); 0 = B.
+// `borders` : 1 / 0 = the caller knows the zero borders of the tensors in `ws` are intact / must be rewritten, -1 = look
+// `ws` up in the network's cache.
 int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, int G, float *out, void *ws, size_t ws_bytes,
-               cudaStream_t st, const TailArgs *tail, int carveB)
+               cudaStream_t st, const TailArgs *tail, int carveB, int borders)
 {
     if (carveB < B) carveB = B;
     const TcNet *tc = net->tc;
@@ -883,7 +888,7 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
     TcCtx c{net, B, st, sms, false};
     const int j1 = tc->layer[L_FRONT0].cin_pad / 8, j2 = tc->layer[L_FRONT0].cout_pad / 8, j4 = tc->layer[L_POOL].cout_pad / 8;
     const uint4 *vol = (const uint4 *)volume_in;
-    const bool borders_valid = net->borders_cached(ws, carveB, G, in_layout);
+    const bool borders_valid = borders >= 0 ? borders != 0 : net->borders_cached(ws, jhn_v2v::border_sig(1 + in_layout, carveB, G, 0, 0));
     if (in_layout != JHN_VOL_V2V_BF16) {
         if (!borders_valid) JHN_TRY(c.zero_border(t.vol_ps, carveB * 8 * j1, h));
         const size_t nv = (size_t)G * G * G;

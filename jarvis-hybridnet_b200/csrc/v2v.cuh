@@ -34,22 +34,29 @@ struct jhn_v2v {
     // mutex, so one handle may serve several streams / threads as long as each has its own workspace.
     mutable std::mutex mu;
     mutable int ws_persistent;
-    struct BorderKey { const void *ptr; int B, G, kind; };
+    struct BorderKey { const void *base; unsigned long long sig; };
     mutable BorderKey zc[16];
     mutable int zc_n;
-    // true iff the borders of the tensors carved from `ptr` for (B, G, kind) are already zero; records the key otherwise
-    bool borders_cached(const void *ptr, int B, int G, int kind) const
+    // One entry per workspace BASE pointer; `sig` encodes everything that decides where tensors lie inside it.  True iff
+    // the workspace was last used with the same carving (its zero borders are intact); records the carving otherwise —
+    // a different carving of the same memory wrote activations over the old borders, so everything is re-zeroed.
+    static unsigned long long border_sig(int kind, int B, int G, int ncam, int hs)
+    {
+        return ((unsigned long long)(kind & 0xf) << 60) | ((unsigned long long)(B & 0xfffff) << 40) |
+               ((unsigned long long)(G & 0x3ff) << 30) | ((unsigned long long)(ncam & 0xfff) << 18) | (unsigned long long)(hs & 0x3ffff);
+    }
+    bool borders_cached(const void *base, unsigned long long sig) const
     {
         std::lock_guard<std::mutex> g(mu);
         if (!ws_persistent) return false;
         for (int i = 0; i < zc_n; ++i)
-            if (zc[i].ptr == ptr && zc[i].kind / 16 == kind / 16) {
-                const bool ok = zc[i].B == B && zc[i].G == G && zc[i].kind == kind;
-                zc[i].B = B; zc[i].G = G; zc[i].kind = kind;
+            if (zc[i].base == base) {
+                const bool ok = zc[i].sig == sig;
+                zc[i].sig = sig;
                 return ok;
             }
         if (zc_n == 16) zc_n = 0;                                // table full: forget everything (costs one re-zeroing each)
-        zc[zc_n++] = BorderKey{ptr, B, G, kind};
+        zc[zc_n++] = BorderKey{base, sig};
         return false;
     }
     void borders_forget() const { std::lock_guard<std::mutex> g(mu); zc_n = 0; }

@@ -43,18 +43,28 @@ class ReprojectionLayer(nn.Module):
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
         return self._ws
 
-    def _run(self, heatmaps, center, centerHM, cam, intr, dist, post_divide=1.0, want_index=False):
-        """heatmaps [B,ncam,K,S,S] with S == heatmap_size (padded) or heatmap_size-2 (un-padded)."""
+    def _run(self, heatmaps, center, centerHM, cam, intr, dist, post_divide=1.0, want_index=False, volume_layout="ncdhw"):
+        """heatmaps [B,ncam,K,S,S] with S == heatmap_size (padded) or heatmap_size-2 (un-padded), or the channels-last
+        16-bit form [B,ncam,hs,hs,24] (torch.float16 scaled by 1/16, or torch.bfloat16; bf16 precision only).
+        volume_layout "v2v" (bf16 precision): the volume stays in the tensor-core convolution's input layout and is
+        returned as an opaque uint8 buffer."""
         lib = _lib.load()
         with _lib.require_cuda(heatmaps, center, centerHM, cam, intr, dist):
-            return self._run_on_device(lib, heatmaps, center, centerHM, cam, intr, dist, post_divide, want_index)
+            return self._run_on_device(lib, heatmaps, center, centerHM, cam, intr, dist, post_divide, want_index, volume_layout)
 
-    def _run_on_device(self, lib, heatmaps, center, centerHM, cam, intr, dist, post_divide, want_index):
-        B, ncam, K, S, S2 = heatmaps.shape
+    def _run_on_device(self, lib, heatmaps, center, centerHM, cam, intr, dist, post_divide, want_index, volume_layout):
         hs, G = self.heatmap_size, self.grid_size
-        if S != S2 or S not in (hs, hs - 2):
-            raise RuntimeError(f"heat maps are {S}x{S2}; expected {hs} (padded) or {hs - 2} per side")
-        hm = heatmaps.contiguous().float()
+        if heatmaps.dtype in (torch.float16, torch.bfloat16):
+            B, ncam, S, S2, P = heatmaps.shape
+            if (S, S2, P) != (hs, hs, _lib.HM_CL_PITCH):
+                raise RuntimeError(f"channels-last heat maps {tuple(heatmaps.shape)} do not match [B,ncam,{hs},{hs},24]")
+            fmt = _lib.HM_F16_CL if heatmaps.dtype == torch.float16 else _lib.HM_BF16_CL
+            hm, K = heatmaps.contiguous(), self.cfg.KEYPOINTDETECT.NUM_JOINTS
+        else:
+            B, ncam, K, S, S2 = heatmaps.shape
+            if S != S2 or S not in (hs, hs - 2):
+                raise RuntimeError(f"heat maps are {S}x{S2}; expected {hs} (padded) or {hs - 2} per side")
+            fmt, hm = _lib.HM_F32_PLANAR, heatmaps.contiguous().float()
         cam = cam.contiguous().float(); intr = intr.contiguous().float(); dist = dist.contiguous().float()
         # `self.grid + center[0]` (repro_layer.py:113) is an fp32 add: an int centre (predictor, jarvis3D.py:183) is
         # promoted exactly, a float centre (validation path, hybridnet.py:284-304) is taken as it is — never truncated
@@ -64,12 +74,21 @@ class ReprojectionLayer(nn.Module):
         need = _lib.c_size_t()
         _lib.check(lib.jhn_reproject_workspace_bytes(B, ncam, K, hs, G, self.precision, need))
         ws = self._workspace(need.value, hm.device)
-        vol = torch.empty((B, K, G, G, G), dtype=torch.float32, device=hm.device)
+        if volume_layout == "v2v":
+            if self.precision != _lib.BF16:
+                raise RuntimeError("the V2V volume layout belongs to the bf16 path")
+            h2, cj = G // 2 + 2, (K + 15) // 16 * 2
+            nbytes = B * 8 * cj * h2 * h2 * h2 * 16
+            if getattr(self, "_vol", None) is None or self._vol.numel() != nbytes or self._vol.device != hm.device:
+                self._vol = torch.zeros(nbytes, dtype=torch.uint8, device=hm.device)      # borders are (re)written by the call
+            vol, layout = self._vol, _lib.VOL_V2V_BF16
+        else:
+            vol, layout = torch.empty((B, K, G, G, G), dtype=torch.float32, device=hm.device), _lib.VOL_NCDHW_F32
         idx = torch.empty((B, ncam, G, G, G), dtype=torch.int32, device=hm.device) if want_index else None
-        _lib.check(lib.jhn_reproject_gather(_lib.dptr(hm), _lib.HM_F32_PLANAR, int(S == hs), _lib.dptr(cam), _lib.dptr(intr),
+        _lib.check(lib.jhn_reproject_gather(_lib.dptr(hm), fmt, int(S == hs), _lib.dptr(cam), _lib.dptr(intr),
                                             _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm), B, ncam, K, hs, G,
                                             float(self.grid_spacing), self.lerp_mode, float(post_divide),
-                                            self.precision, _lib.VOL_NCDHW_F32, _lib.dptr(vol), _lib.dptr(idx),
+                                            self.precision, layout, _lib.dptr(vol), _lib.dptr(idx),
                                             _lib.dptr(ws), ws.numel(), _lib.stream_ptr()))
         return vol, idx
 
@@ -90,7 +109,7 @@ class ReprojectionLayer(nn.Module):
         return vol
 
     def forward_batched(self, heatmaps, center, centerHM, cameraMatrices, intrinsicMatrices,
-                        distortionCoefficients, post_divide=1.0, want_index=False):
+                        distortionCoefficients, post_divide=1.0, want_index=False, volume_layout="ncdhw"):
         """All B frame sets in one launch sequence -> ([B,K,G,G,G] fp32, optional int32 indices)."""
         return self._run(heatmaps, center, centerHM, cameraMatrices, intrinsicMatrices, distortionCoefficients,
-                         post_divide, want_index)
+                         post_divide, want_index, volume_layout)

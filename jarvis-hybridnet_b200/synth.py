@@ -123,6 +123,17 @@ def make_frameset(shape, cam, intr, dist, seed=0, noise=2.0, dtype=np.float32):
     return g.astype(dtype), center3D, chm.astype(np.int32), kps
 
 
+def to_cl16(hm, scale=0.0625, dtype=np.float16, pitch=24):
+    """Host-side producer of the gather-native heat-map layout (include/jarvis_hybridnet_b200.h, JHN_HM_F16_CL): un-padded
+    planar maps [..., ncam, K, S, S] -> channels-last [..., ncam, S+2, S+2, 24] with the F.pad border
+    (jarvis/hybridnet/model.py:65-66) materialised and the values scaled by 2^-4."""
+    hm = np.asarray(hm)
+    K, S = hm.shape[-3], hm.shape[-1]
+    out = np.zeros(hm.shape[:-3] + (S + 2, S + 2, pitch), dtype)
+    out[..., 1:-1, 1:-1, :K] = (np.moveaxis(hm, -3, -1) * np.float32(scale)).astype(dtype)
+    return out
+
+
 V2V_LAYERS = (
     # (state_dict prefix under v2vNet., kind, cin_mult, cout_mult, kernel)   v2vnet.py:62-96
     ("front_layers.0.block.0", "conv", 1, 2, 3),

@@ -20,7 +20,9 @@ __global__ void probe(const int *units, int npat, long long *out, int iters, int
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const uint4 v = sm[(u + 64 * k) & 4095];        // +64 units = +1024 B keeps every bank group
+                uint4 v;                                         // +64 units = +1024 B keeps every bank group
+                const uint32_t addr = (uint32_t)__cvta_generic_to_shared(sm + ((u + 64 * k) & 4095));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
                 acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
             }
         }
