@@ -25,7 +25,6 @@
 //                          pixel boxes of a channels-last fp16 staging copy are TMA-staged in shared memory and
 //                          gathered with LDS.128; see the block comment above the kernel.
 #include <atomic>
-#include <cstdlib>
 
 #include <cuda_fp16.h>
 
@@ -475,6 +474,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16cg(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -755,293 +758,7 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Streaming gather, second form ("block gather").  Same work items, same pixel boxes, same index arithmetic as
-// gather_stream_kernel above, reorganised around how the shared-memory pipe really prices an LDS.128
-// (tools/lds_bench.cu, profiles/r02_lds_bench.txt): a quarter-warp pays one wavefront per distinct 16-byte unit
-// that collides in a bank group, two conflict-free quarters of a half-warp whose units do not collide either share ONE
-// wavefront, and identical addresses are free.  A z run of 8 voxels per quarter (the first form) touches up to 8 pixels
-// along a line and costs 5.8 wavefronts per load on the Example rig; a 2x2x2 voxel cube per quarter / 2x2x4 block per
-// half-warp touches 2-6 neighbouring pixels, and with a row pitch == 3 (mod 8) pixels a 3x3 pixel neighbourhood maps
-// to distinct bank groups: 3.3 wavefronts per load with NO per-item pitch search (simulated on the reference's exact
-// indices, tests/sim_gather_conflicts.py).  The lane <-> voxel map that makes the loads cheap is the opposite of the
-// one that shares the trilinear lerps, so the two jobs are split:
-//   producer warp (4 per CTA, one item each, setmaxnreg 88): corners (LDGSTS, prefetched one item ahead) -> pixel box
-//       (REDUX) -> TMA rows of the box -> while they fly, lane (cx, cy, zh) evaluates the index chain for its two 2x2x2
-//       cubes (16 voxels share 16 corner pairs: 8 LDS.128) and writes 16 byte offsets into the slot's offset table
-//       (4 STS.128, rows padded to 144 B: conflict-free) -> mbarrier.arrive; the box bytes complete the same barrier.
-//   gather warp (4 per CTA, setmaxnreg 96): thread = 4 voxels, one per 2x2x4 block; per item and voxel ONE LDS.32 of the
-//       offset, 3 x LDS.128, 12 x HADD2.  After the last camera: fp32 scale, bf16 pack, 16-byte stores.
-// ------------------------------------------------------------------------------------------------
-constexpr int GB_OFF_PITCH = 36;                                               // u32 per (cx, cy) row of the offset table: 32 + 4 pad (144 B)
-constexpr int GB_OFF_BYTES = 16 * GB_OFF_PITCH * 4;                            // per slot
-constexpr uint32_t GB_INVALID = 0xffffffffu;
-
-__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-template <int LAYOUT, int MODE>
-__global__ void __launch_bounds__(GS_THREADS, 3)
-gather_block_kernel(const __half *__restrict__ hm, const float2 *__restrict__ cab,
-                    int ncam, int K, int hs, int G, float post_scale, int cap_bytes, int box_limit, void *__restrict__ out_, int total_tiles)
-{
-    extern __shared__ __align__(128) uint8_t gsm[];                            // [GS_SLOTS][cap_bytes] pixel boxes
-    uint32_t *offs = reinterpret_cast<uint32_t *>(gsm + (size_t)GS_SLOTS * cap_bytes);      // [GS_SLOTS][16][GB_OFF_PITCH]
-    uint8_t *hdrs = reinterpret_cast<uint8_t *>(offs) + GS_SLOTS * GB_OFF_BYTES;            // [2 * GS_SLOTS][GS_HDR] corners; int4 meta at GS_META
-    uint64_t *bars = reinterpret_cast<uint64_t *>(hdrs + 2 * GS_SLOTS * GS_HDR);
-    uint64_t *full = bars, *empty = bars + GS_SLOTS;
-    const int h = G / 2, nt = G / GT + 1, ntk = G / GT, tiles_fs = nt * nt * ntk;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t nc = (size_t)h * h * h;
-    const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < GS_SLOTS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp >= 4) {
-        // =================================== producers ========================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");                  // 72 + 88 (gather warps) = 2 x the 80 registers of the launch
-        const int p = warp - 4;
-        const int total = my_tiles * ncam;
-        int go[GS_CORNERS_PER_LANE];
-        int go_tl = -1;
-        const float2 *csrc = cab;
-        auto prefetch = [&](int n) {                                           // corners of item n -> its header (LDGSTS)
-            const int tl = n / ncam, c = n - tl * ncam;
-            if (tl != go_tl) {
-                go_tl = tl;
-                const int t = (int)blockIdx.x + tl * (int)gridDim.x;
-                const int b = t / tiles_fs, r0 = t - b * tiles_fs;
-                const int tk = r0 % ntk, tj = (r0 / ntk) % nt, ti = r0 / (ntk * nt);
-                tile_corner_offsets(lane, ti, tj, tk, h, go);
-                csrc = cab + (size_t)b * ncam * nc;
-            }
-            const float2 *src = csrc + (size_t)c * nc;
-            const uint32_t dst = smem_u32(hdrs + (n % (2 * GS_SLOTS)) * GS_HDR);
-#pragma unroll
-            for (int r = 0; r < GS_CORNERS_PER_LANE; ++r)
-                if (lane + 32 * r < GCN) cp_async8(dst + (uint32_t)(lane + 32 * r) * 8u, src + go[r]);
-            cp_async_commit();
-        };
-        // this lane's two cubes: (cx, cy, cz = 2 zh + e), e = 0, 1
-        const int zh = lane >> 4, cx = (lane >> 2) & 3, cy = lane & 3;
-        const uint64_t whalf = f2_pack(0.5f, 0.5f);
-        if (p < total) prefetch(p);
-        uint32_t ph = 0;
-        for (int n = p; n < total; n += GS_SLOTS) {
-            cp_async_wait<0>();
-            __syncwarp();                                                      // all lanes' copies visible to all lanes
-            const uint8_t *hd = hdrs + (n % (2 * GS_SLOTS)) * GS_HDR;
-            int x0, x1, y0, y1;
-            {
-                const float2 *cn = reinterpret_cast<const float2 *>(hd);
-                const float2 v0 = cn[lane];
-                x0 = x1 = __float2int_rz(__fmul_rn(v0.x, 0.5f)); y0 = y1 = __float2int_rz(__fmul_rn(v0.y, 0.5f));
-#pragma unroll
-                for (int r = 1; r < GS_CORNERS_PER_LANE; ++r) {
-                    const int l = lane + 32 * r;
-                    const float2 v = cn[l < GCN ? l : lane];
-                    const int px = __float2int_rz(__fmul_rn(v.x, 0.5f)), py = __float2int_rz(__fmul_rn(v.y, 0.5f));
-                    x0 = min(x0, px); x1 = max(x1, px); y0 = min(y0, py); y1 = max(y1, py);
-                }
-                x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
-                y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
-            }
-            const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
-            int pitch = bw + ((3 - bw) & 7);                                   // smallest pitch >= bw with pitch == 3 (mod 8)
-            if (pitch * bh * G_PIX_BYTES > box_limit) pitch = bw;
-            if (pitch * bh * G_PIX_BYTES > box_limit || x0 < 0 || y0 < 0 || x1 >= hs || y1 >= hs) pitch = 0;   // 0: gathered from global memory
-            const int tl = n / ncam, c = n - tl * ncam;
-            const int t = (int)blockIdx.x + tl * (int)gridDim.x;
-            const int b = t / tiles_fs, r0 = t - b * tiles_fs;
-            const int tk = r0 % ntk, tj = (r0 / ntk) % nt, ti = r0 / (ntk * nt);
-            const uint32_t fb = smem_u32(full + p);
-            if (n >= GS_SLOTS) { mbar_wait_parked(smem_u32(empty + p), ph); ph ^= 1u; }   // item n - GS_SLOTS done: box, offsets, meta free
-            if (pitch) {
-                const uint32_t row_bytes = (uint32_t)(bw * G_PIX_BYTES);
-                if (lane == 0) mbar_expect_tx_only(fb, row_bytes * (uint32_t)bh);
-                __syncwarp();
-                uint8_t *box = gsm + (size_t)p * cap_bytes;
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(hm) + ((((size_t)b * ncam + c) * hs + y0) * hs + x0) * G_PIX_BYTES;
-                const int rowB = pitch * G_PIX_BYTES;
-                for (int r = lane; r < bh; r += 32)
-                    bulk_load(smem_u32(box + (size_t)r * rowB), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
-            }
-            if (n + GS_SLOTS < total) prefetch(n + GS_SLOTS);                  // into this producer's other header
-
-            // ---- index chain of this lane's 2 x (2x2x2) voxels (repro_layer.py:70-83), byte offsets into the box / the map
-            const int rowB = (pitch ? pitch : hs) * G_PIX_BYTES;
-            const int baseB = pitch ? p * cap_bytes - (y0 * pitch + x0) * G_PIX_BYTES : 0;
-            const int I0 = GT * ti - 1 + 2 * cx, J0 = GT * tj - 1 + 2 * cy;
-            uint64_t wj1[2], wj0[2], wi1[2], wi0[2];
-            bool vi[2], vj[2];
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                // ATen area_pixel_compute_source_index, scale .5: even fine index -> lambda1 .75, odd -> .25, index 0 -> 0
-                const float j1 = (J0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f), j0 = __fsub_rn(1.f, j1);
-                const float i1 = (I0 + v) == 0 ? 0.f : (v ? 0.75f : 0.25f), i0 = __fsub_rn(1.f, i1);
-                wj1[v] = f2_pack(j1, j1); wj0[v] = f2_pack(j0, j0); wi1[v] = f2_pack(i1, i1); wi0[v] = f2_pack(i0, i0);
-                vi[v] = (I0 + v) >= 0 && (I0 + v) < G; vj[v] = (J0 + v) >= 0 && (J0 + v) < G;
-            }
-            uint64_t C4[2][2][4];                                              // corner pairs (x, y) [p][q][lk - 2 zh]
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(hd + (size_t)((((cx + pp) * GC + (cy + q)) * GCK + 2 * zh) * 8));
-                    const ulonglong2 a = src[0], bq = src[1];
-                    C4[pp][q][0] = a.x; C4[pp][q][1] = a.y; C4[pp][q][2] = bq.x; C4[pp][q][3] = bq.y;
-                }
-            uint32_t o16[16];
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-#pragma unroll
-                for (int kv = 0; kv < 2; ++kv) {
-                    const int Kz = GT * tk + 4 * zh + 2 * e + kv;
-                    const float lk1 = Kz == 0 ? 0.f : (kv ? 0.25f : 0.75f), lk0w = __fsub_rn(1.f, lk1);
-                    const uint64_t wk0 = f2_pack(lk0w, lk0w), wk1 = f2_pack(lk1, lk1);
-                    uint64_t xk[2][2];
-#pragma unroll
-                    for (int pp = 0; pp < 2; ++pp)
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) xk[pp][q] = lerp2<MODE>(wk0, C4[pp][q][e + kv], wk1, C4[pp][q][e + kv + 1]);
-#pragma unroll
-                    for (int jv = 0; jv < 2; ++jv) {
-                        uint64_t yj[2];
-#pragma unroll
-                        for (int pp = 0; pp < 2; ++pp) yj[pp] = lerp2<MODE>(wj0[jv], xk[pp][0], wj1[jv], xk[pp][1]);
-#pragma unroll
-                        for (int iv = 0; iv < 2; ++iv) {
-                            float fa, fb2;
-                            f2_unpack(f2_mul(lerp2<MODE>(wi0[iv], yj[0], wi1[iv], yj[1]), whalf), fa, fb2);
-                            const int px = __float2int_rz(fa), py = __float2int_rz(fb2);            // (val/2).int()   repro_layer.py:82-83
-                            const uint32_t off = (uint32_t)(py * rowB + (px * G_PIX_BYTES + baseB));
-                            o16[e * 8 + kv * 4 + jv * 2 + iv] = (vi[iv] && vj[jv]) ? off : GB_INVALID;
-                        }
-                    }
-                }
-            {
-                uint4 *dst = reinterpret_cast<uint4 *>(offs + (size_t)p * (GB_OFF_BYTES / 4) + (cx * 4 + cy) * GB_OFF_PITCH + zh * 16);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(o16[4 * i], o16[4 * i + 1], o16[4 * i + 2], o16[4 * i + 3]);
-            }
-            if (lane == 0) *reinterpret_cast<int4 *>(hdrs + (size_t)p * GS_HDR + GS_META) = make_int4(pitch, b * ncam + c, 0, 0);
-            __syncwarp();                                                      // every lane's offsets + the meta precede the arrive
-            if (lane == 0) mbar_arrive(fb);
-        }
-        return;
-    }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-
-    // =================================== gather warps ========================================
-    // thread = 4 voxels: cube (cx = warp, cy = i, cz = lane >> 3), voxel (dx, dy, dz) = lane & 7 bits
-    const int dx = lane & 1, dy = (lane >> 1) & 1, lz = 2 * (lane >> 3) + ((lane >> 2) & 1);
-    const size_t nv = (size_t)G * G * G;
-    int s = 0; uint32_t ph = 0;
-    for (int tl = 0; tl < my_tiles; ++tl) {
-        const int t = (int)blockIdx.x + tl * (int)gridDim.x;
-        const int b = t / tiles_fs, r0 = t - b * tiles_fs;
-        const int tk = r0 % ntk, tj = (r0 / ntk) % nt, ti = r0 / (ntk * nt);
-        const int I = GT * ti - 1 + 2 * warp + dx, Kz = GT * tk + lz;
-        const bool vI = I >= 0 && I < G;
-        const bool warp_live = (GT * ti - 1 + 2 * warp + 1) >= 0 && (GT * ti - 1 + 2 * warp) < G;     // some x of this warp's cubes inside the grid
-        __half2 acc[4][KP / 2];
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-#pragma unroll
-            for (int i = 0; i < KP / 2; ++i) acc[v][i] = __float2half2_rn(0.f);
-
-        for (int c = 0; c < ncam; ++c) {
-            mbar_wait(smem_u32(full + s), ph);
-            if (warp_live) {
-                const int4 meta = *reinterpret_cast<const int4 *>(hdrs + (size_t)s * GS_HDR + GS_META);
-                const uint32_t *orow = offs + (size_t)s * (GB_OFF_BYTES / 4) + warp * 4 * GB_OFF_PITCH + lane;
-                uint32_t off[4];
-#pragma unroll
-                for (int v = 0; v < 4; ++v) off[v] = orow[v * GB_OFF_PITCH];
-                const uint8_t *gbase = reinterpret_cast<const uint8_t *>(hm) + (size_t)meta.y * hs * hs * G_PIX_BYTES;
-                const bool in_smem = meta.x != 0;                              // warp-uniform: LDS from the staged box, else LDG from the map
-#pragma unroll
-                for (int v0 = 0; v0 < 4; v0 += 2) {                            // two voxels (6 x 16 B) in flight per thread
-                    uint4 w[2][3];
-#pragma unroll
-                    for (int v = 0; v < 2; ++v) {
-                        w[v][0] = w[v][1] = w[v][2] = make_uint4(0, 0, 0, 0);
-                        if (off[v0 + v] != GB_INVALID) {
-                            if (in_smem) {
-                                const uint32_t a = smem_u32(gsm) + off[v0 + v];
-                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[v][0].x), "=r"(w[v][0].y), "=r"(w[v][0].z), "=r"(w[v][0].w) : "r"(a));
-                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(w[v][1].x), "=r"(w[v][1].y), "=r"(w[v][1].z), "=r"(w[v][1].w) : "r"(a));
-                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(w[v][2].x), "=r"(w[v][2].y), "=r"(w[v][2].z), "=r"(w[v][2].w) : "r"(a));
-                            } else {
-                                const uint4 *pp = reinterpret_cast<const uint4 *>(gbase + off[v0 + v]);
-                                w[v][0] = __ldg(pp); w[v][1] = __ldg(pp + 1); w[v][2] = __ldg(pp + 2);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int v = 0; v < 2; ++v)
-#pragma unroll
-                        for (int g = 0; g < 3; ++g) {
-                            const uint32_t ww[4] = {w[v][g].x, w[v][g].y, w[v][g].z, w[v][g].w};
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                acc[v0 + v][4 * g + i] = __hadd2(acc[v0 + v][4 * g + i], *reinterpret_cast<const __half2 *>(&ww[i]));
-                        }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(empty + s));
-            if (++s == GS_SLOTS) { s = 0; ph ^= 1u; }
-        }
-
-        // ---- mean over cameras (+ /255) as one fp32 scale, store ---------------------------------------
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const int J = GT * tj - 1 + 2 * v + dy;
-            if (!(vI && J >= 0 && J < G)) continue;
-            float m[KP];
-#pragma unroll
-            for (int i = 0; i < KP / 2; ++i) {
-                const float2 f = __half22float2(acc[v][i]);
-                m[2 * i] = f.x * post_scale; m[2 * i + 1] = f.y * post_scale;
-            }
-            if (LAYOUT == JHN_VOL_NCDHW_F32) {
-                float *out = (float *)out_ + (size_t)b * K * nv + ((size_t)I * G + J) * G + Kz;
-#pragma unroll
-                for (int k = 0; k < KP; ++k)
-                    if (k < K) out[(size_t)k * nv] = m[k];
-            } else {
-                const int CJ = (K + 15) / 16 * 2, Wh = G / 2 + 2;
-                const int sv = ((I & 1) * 2 + (J & 1)) * 2 + (Kz & 1);
-                uint4 *out = (uint4 *)out_;
-                const size_t pos = ((size_t)(I >> 1) + 1) * Wh * Wh + (size_t)((J >> 1) + 1) * Wh + (Kz >> 1) + 1;
-                const size_t chunk_stride = (size_t)Wh * Wh * Wh;
-                const size_t ob = (((size_t)b * 8 + sv) * CJ) * chunk_stride + pos;
-#pragma unroll
-                for (int j = 0; j < KP / 8; ++j) {
-                    if (j < CJ) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(m[8 * j + 2 * i], m[8 * j + 2 * i + 1]);
-                            pk[i] = *reinterpret_cast<uint32_t *>(&h2);
-                        }
-                        out[ob + (size_t)j * chunk_stride] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    }
-                }
-            }
-        }
-    }
-}
-
-constexpr int GS_CAP = 15360;                                                  // bytes per pixel-box slot of the streaming kernel (first form)
-constexpr int GB_CAP = 14080;                                                  // second form: 3 CTAs x (4 boxes + offsets + headers) fill the SM's shared memory
+constexpr int GS_CAP = 15360;                                                  // bytes per pixel-box slot of the streaming kernel
 static std::atomic<int> g_box_limit{GS_CAP};                                   // boxes above this gather from global memory (test hook)
 int gather_set_box_bytes(int bytes)
 {
@@ -1053,9 +770,7 @@ int gather_set_box_bytes(int bytes)
 template <int LAYOUT>
 static int launch_stream(const ReprojectArgs &a, const __half *hm_cl, const float2 *cab, int cap, cudaStream_t st)
 {
-    static const bool v1 = [] { const char *e = getenv("JHN_GATHER_V1"); return e && e[0] == '1'; }();   // A/B switch: first form of the kernel
-    if (v1) cap = GS_CAP;
-    const size_t gsmem = (size_t)GS_SLOTS * cap + (v1 ? 0 : GS_SLOTS * GB_OFF_BYTES) + 2 * GS_SLOTS * GS_HDR + 2 * GS_SLOTS * 8;
+    const size_t gsmem = (size_t)GS_SLOTS * cap + 2 * GS_SLOTS * GS_HDR + 2 * GS_SLOTS * 8;
     const int nt = a.G / GT + 1, ntk = a.G / GT;
     const long long total = (long long)a.B * nt * nt * ntk;
     if (total * a.ncam > 0x7fffffffLL) return fail(JHN_ERR_SHAPE, "too many gather tiles (%lld)", total);
@@ -1069,7 +784,7 @@ static int launch_stream(const ReprojectArgs &a, const __half *hm_cl, const floa
     if (box_limit > cap) box_limit = cap;
 #define JHN_STREAM(MODE)                                                                                         \
     {                                                                                                            \
-        auto kern = v1 ? gather_stream_kernel<LAYOUT, MODE> : gather_block_kernel<LAYOUT, MODE>;                 \
+        auto kern = gather_stream_kernel<LAYOUT, MODE>;                                                          \
         JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));           \
         JHN_LAUNCH("gather_stream_kernel", st,                                                                   \
                    kern<<<grid, GS_THREADS, gsmem, st>>>(hm_cl, cab, a.ncam, a.K, a.hs, a.G, post_scale, cap, \
@@ -1158,7 +873,7 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
             JHN_LAUNCH("relayout_kernel", st,
                        bf16cl_to_f16cl_kernel<<<cdiv((long long)n16, 256), 256, 0, st>>>((const uint4 *)a.heatmaps, (uint4 *)hm_cl, n16));
         }
-        if (a.layout == JHN_VOL_NCDHW_F32) return launch_stream<JHN_VOL_NCDHW_F32>(a, src16, cab, GB_CAP, st);
+        if (a.layout == JHN_VOL_NCDHW_F32) return launch_stream<JHN_VOL_NCDHW_F32>(a, src16, cab, GS_CAP, st);
         const int CJ = (a.K + 15) / 16 * 2;
         if (!a.borders_valid) {
             JHN_TRY(tc_zero_border_launch(a.volume_out, a.B * 8 * CJ, a.G / 2, st));
@@ -1168,7 +883,7 @@ int reproject_launch(const ReprojectArgs &a, void *ws, size_t ws_bytes, cudaStre
                                            (CJ - KP / 8) * chunk_bytes, (size_t)a.B * 8, st));
             }
         }
-        return launch_stream<JHN_VOL_V2V_BF16>(a, src16, cab, GB_CAP, st);
+        return launch_stream<JHN_VOL_V2V_BF16>(a, src16, cab, GS_CAP, st);
     }
     if (a.hm_format == JHN_HM_F16_CL) return run_gather<__half>(a, (const __half *)a.heatmaps, cab, st);
     if (a.hm_format == JHN_HM_BF16_CL) return run_gather<__nv_bfloat16>(a, (const __nv_bfloat16 *)a.heatmaps, cab, st);

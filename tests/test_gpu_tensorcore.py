@@ -269,7 +269,7 @@ def test_sub_batch_invariance():
             outs[sb] = [t.clone() for t in net(*args)]
         for sb in (3, 2, 1):
             assert (outs[sb][0] - outs[7][0]).abs().max().item() < 5e-3, sb
-            assert torch.allclose(outs[sb][1], outs[7][1], rtol=0, atol=1e-4)
+            assert torch.allclose(outs[sb][1], outs[7][1], rtol=0, atol=5e-4)
         one = [net(*[a[b:b + 1] for a in args])[0] for b in range(7)]
         assert torch.equal(torch.cat(one), outs[1][0])              # pass size 1 == seven B=1 calls, bit for bit
     finally:
