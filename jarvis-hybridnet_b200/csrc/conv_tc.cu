@@ -17,11 +17,16 @@
 // epilogue scatters to the 8 output parities.
 //
 // Kernel: persistent, warp-specialised, one CTA per SM.
-//     warp 0     TMA producer (one elected lane): cp.async.bulk of activation boxes (+ weight slabs when
-//                not resident) into a ring of shared-memory slots, completion on mbarriers
-//     warp 1     TMEM allocator + MMA issuer (one elected lane): tcgen05.mma M=128, N=Cout_pad, K=16,
-//                descriptors formed from a per-tile offset list precomputed in shared memory
-//     warps 2-9  epilogue, two per TMEM lane quadrant on alternate 16-column chunks: tcgen05.ld -> bias -> pad mask -> bf16 store and
+//     warps 0-3  TMA producers (one elected lane each): cp.async.bulk of activation boxes (+ weight slabs when not
+//                resident) into a ring of shared-memory slots, completion on mbarriers
+//     warps 4-7  MMA issuers (one elected lane each; warp 4 also allocates TMEM): tcgen05.mma M=128, N=Cout_pad, K=16,
+//                descriptors formed from a per-tile offset list precomputed in shared memory.
+//                Producer r, ring share r, issuer r and accumulator buffer r form pipeline r; tile i of the CTA goes to
+//                pipeline i % npipe.  One producer / issuer thread per CTA was the bound of the k3 s2 front convolution:
+//                each spent ~100 dependent instructions per stage (12 stages per tile), 70-80 % of its cycles issuing
+//                (profiles/r02_tc_conv_front_ncu.txt).  npipe = 4 when the ring has >= 8 slots and 4 accumulator buffers
+//                fit TMEM, else 2, else 1.
+//     warps 8-15 epilogue, two per TMEM lane quadrant on alternate 16-column chunks: tcgen05.ld -> bias -> pad mask -> bf16 store and
 //                per-channel sum / sum-of-squares for the following InstanceNorm (fused statistics)
 // Weights of the C->C 3x3x3 layers (124 KB bf16) stay resident in shared memory for the CTA's lifetime.
 // The work of a layer is a "stage program" (TcProgram) built on the host: per tile a list of TMA boxes and,
@@ -74,13 +79,14 @@ struct TcLaunch {
 // ------------------------------------------------------------------------------------------------
 // the implicit-GEMM kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 320;                      // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int TC_PIPES = 4;                          // producer / issuer warp pairs, each with its own ring share and accumulator buffer
+constexpr int TC_THREADS = 32 * (2 * TC_PIPES + 8);  // TC_PIPES TMA warps, TC_PIPES MMA warps, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int TC_EPI_WARPS = 8;
 constexpr int EPI_TILE_FLOATS = 32 * 17;
 constexpr int TC_MAX_SLOTS = 16;                       // ring depth: bytes in flight per SM = slots x box; 8 slots of the
                                                       // 10 KB front-conv boxes cover only ~2/3 of the L2 latency-bandwidth product
 constexpr int MAX_DESC = 1024;                         // descriptor pairs: (MMAs per tile) x (ring slots)
-constexpr int TC_SMEM_TAIL = TC_EPI_WARPS * EPI_TILE_FLOATS * 4 + 128 * 4 + (2 * TC_MAX_SLOTS + 14) * 8 + MAX_DESC * 8 + 1024;
+constexpr int TC_SMEM_TAIL = TC_EPI_WARPS * EPI_TILE_FLOATS * 4 + 128 * 4 + (2 * TC_MAX_SLOTS + 2 * 4 + 10) * 8 + MAX_DESC * 8 + 1024;
 
 struct TileCoord { int b, z, pt, tap; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const TcLaunch &L, int tile_taps)
@@ -110,24 +116,27 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
     float *epi_tiles = reinterpret_cast<float *>(ring + (size_t)P.nslots * P.stage_bytes);
     float *bias_s = epi_tiles + TC_EPI_WARPS * EPI_TILE_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + 128);
-    uint64_t *full = bars, *empty = bars + TC_MAX_SLOTS, *tfull = bars + 2 * TC_MAX_SLOTS, *tempty = tfull + 2, *wbar = tfull + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfull + 5);
-    int *stage_first = reinterpret_cast<int *>(tfull + 6);            // [MAX_STAGES + 1]
-    uint2 *desc_list = reinterpret_cast<uint2 *>(tfull + 14);         // [nslots][MMAs per tile] (A desc lo, B desc lo)
+    uint64_t *full = bars, *empty = bars + TC_MAX_SLOTS, *tfull = bars + 2 * TC_MAX_SLOTS, *tempty = tfull + TC_PIPES, *wbar = tfull + 2 * TC_PIPES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wbar + 1);
+    int *stage_first = reinterpret_cast<int *>(wbar + 2);             // [MAX_STAGES + 1]
+    uint2 *desc_list = reinterpret_cast<uint2 *>(wbar + 10);          // [nslots][MMAs per tile] (A desc lo, B desc lo)
 
     // contiguous tile range of this CTA
     const int t_begin = (int)((long long)L.total_tiles * blockIdx.x / gridDim.x);
     const int t_end = (int)((long long)L.total_tiles * (blockIdx.x + 1) / gridDim.x);
     // TMEM: 2 tile buffers x 2 interleaved accumulators (the K loop of a tile alternates between two
     // independent accumulation chains; the epilogue adds them) x NOUT fp32 columns
-    const uint32_t tmem_need = 4u * (uint32_t)P.NOUT;
+    // pipelines: each needs >= 2 ring slots and an accumulator buffer of 2 x NOUT columns (two interleaved accumulation chains)
+    const int npipe = (P.nslots >= 8 && 8 * P.NOUT <= 512) ? 4 : (P.nslots >= 4 ? 2 : 1);
+    const int nbuf = npipe > 2 ? npipe : 2;                           // accumulator buffers
+    const uint32_t tmem_need = (uint32_t)(nbuf * 2 * P.NOUT);
     const uint32_t tmem_cols = tmem_need <= 32 ? 32 : tmem_need <= 64 ? 64 : tmem_need <= 128 ? 128 : tmem_need <= 256 ? 256 : 512;
 
     bool dual = true;                                 // second accumulator is written in every stage?
     for (int s = 0; s < P.nstages; ++s) dual = dual && (P.st[s].ntaps * (P.KC / 2) >= 2);
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.nslots; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), TC_EPI_WARPS); }
+        for (int i = 0; i < TC_PIPES; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), TC_EPI_WARPS); }
         mbar_init(smem_u32(wbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -141,7 +150,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == TC_PIPES) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -150,18 +159,22 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // =================================== TMA producer ===================================
+    if (warp < TC_PIPES) {
+        // =================================== TMA producers ==================================
         if (elect_one()) {
-            if (P.resident) {
+            if (P.resident && warp == 0) {
                 mbar_expect_tx(smem_u32(wbar), (uint32_t)P.w_bytes);
                 for (int off = 0; off < P.w_bytes; off += 32768) {
                     const int n = min(32768, P.w_bytes - off);
                     bulk_load(smem_u32(w_smem + off), reinterpret_cast<const uint8_t *>(L.w) + off, n, smem_u32(wbar));
                 }
             }
-            int slot = 0; uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
+            // two independent pipelines (producer r -> ring half r -> issuer r -> accumulator buffer r) on alternate tiles: each
+            // is a strictly sequential single-producer / single-consumer ring, so the one-bit phase parity of its mbarriers
+            // stays unambiguous.  Rings of fewer than 4 slots (the streamed 96-channel layers) run as one pipeline.
+            const int nsl = P.nslots / npipe, slot0 = warp * nsl;
+            int slot = slot0; uint32_t phase = 0;
+            for (int t = t_begin + warp; warp < npipe && t < t_end; t += npipe) {
                 const TileCoord c = decode_tile(t, L, P.tile_taps);
                 const int p0 = Wp + 1 + c.pt * TILE_M;
                 for (int s = 0; s < P.nstages; ++s) {
@@ -186,12 +199,12 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
                         bulk_load(smem_u32(dst + P.stage_bytes_a),
                                   reinterpret_cast<const uint8_t *>(L.w) + (size_t)S.wtap0 * tap_bytes,
                                   (uint32_t)(S.ntaps * tap_bytes), fb);
-                    if (++slot == P.nslots) { slot = 0; phase ^= 1; }
+                    if (++slot == slot0 + nsl) { slot = slot0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // =================================== MMA issuer ======================================
+    } else if (warp < 2 * TC_PIPES) {
+        // =================================== MMA issuers =====================================
         // Flatten the stage program into complete descriptor low words, one (A, B) pair per MMA and ring slot,
         // so that the issue loop is LDS.64 -> 2x R2UR -> UTCHMMA.  Descriptor words: lo = start address
         // (16-byte units) | LBO << 16, hi = SBO (= 8 units, 128 B) | version 1.
@@ -227,9 +240,10 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
             const uint64_t hi_c = (uint64_t)(8u | (1u << 14)) << 32;
             const uint32_t nout = (uint32_t)P.NOUT;
             if (P.resident) mbar_wait(smem_u32(wbar), 0);
-            int slot = 0; uint32_t phase = 0;
-            int ab = 0; uint32_t aphase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
+            const int nsl = P.nslots / npipe, pipe = warp - TC_PIPES, slot0 = pipe * nsl;
+            int slot = slot0; uint32_t phase = 0;
+            int ab = pipe; uint32_t aphase = 0;                      // npipe > 1: issuer r owns accumulator buffer r; one pipeline: it alternates between two
+            for (int t = t_begin + pipe; pipe < npipe && t < t_end; t += npipe) {
                 const uint32_t tile_b = P.tile_taps > 1 ? (uint32_t)(t % P.tile_taps) * tap_units : 0u;
                 mbar_wait(smem_u32(tempty + ab), aphase ^ 1);
                 tc_fence_after();
@@ -256,10 +270,11 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
                         acc0 = 1;
                     }
                     tc_commit(smem_u32(empty + slot));               // frees the smem slot when the MMAs retire
-                    if (++slot == P.nslots) { slot = 0; phase ^= 1; }
+                    if (++slot == slot0 + nsl) { slot = slot0; phase ^= 1; }
                 }
                 tc_commit(smem_u32(tfull + ab));                     // accumulator ready for the epilogue
-                if (++ab == 2) { ab = 0; aphase ^= 1; }
+                if (npipe > 1) aphase ^= 1;
+                else if (++ab == 2) { ab = 0; aphase ^= 1; }
             }
         }
     } else {
@@ -267,9 +282,9 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
         // two warps per TMEM lane quadrant (warp % 4), taking alternate 16-column chunks: the per-tile chain
         // tcgen05.ld -> pack -> store -> statistics is latency-bound, so a second warp per scheduler halves it
         const int wq = warp & 3;                                     // TMEM lane quarter this warp may read
-        const int chalf = (warp - 2) >> 2;                           // which chunks: ci % 2 == chalf
+        const int chalf = (warp - 2 * TC_PIPES) >> 2;                // which chunks: ci % 2 == chalf
         const int m = wq * 32 + lane;                                // GEMM row == position offset in the tile
-        float *tile = epi_tiles + (warp - 2) * EPI_TILE_FLOATS;
+        float *tile = epi_tiles + (warp - 2 * TC_PIPES) * EPI_TILE_FLOATS;
         const int col = lane & 15, which = lane >> 4;                // statistics ownership
         float acc_stat[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int stat_b = -1;
@@ -359,13 +374,13 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty + ab));
-            if (++ab == 2) { ab = 0; aphase ^= 1; }
+            if (++ab == nbuf) { ab = 0; aphase ^= 1; }
         }
         if (L.stats.part && stat_b >= 0) flush_stats(stat_b);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == TC_PIPES) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
