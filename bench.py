@@ -398,6 +398,59 @@ def torch_reference_gpu(sh, weights, batch, n_frame_sets=8, reps=3):
     return out
 
 
+def reference_modules_gpu(sh, weights, batch, n_frame_sets=8, reps=3):
+    """The UNMODIFIED reference modules on this GPU (baseline leg; needs the pip-installed copy under baseline/_ref, see
+    baseline/ref_shim.py): HybridNetBackbone built by its own constructor (jarvis/hybridnet/model.py:20-50), this run's V2V
+    weights loaded with strict=True, effTrack replaced by a stub returning the resident heat maps (the 2D CNN is outside
+    the timed region for both arms), called one frame set at a time as predict3D does (predict3D.py:75-97).  Returns None
+    when the install is absent."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_shim
+        if not ref_shim.import_reference():
+            return None
+        from jarvis.hybridnet.model import HybridNetBackbone
+    except Exception as e:                                              # a baseline leg must not take the bench down
+        return dict(error=str(e)[:200])
+    hm_b, c3_b, chm_b, cam_b, intr_b, dist_b = batch
+    bb = HybridNetBackbone(ref_shim.make_cfg(sh.ncam, sh.K, sh.bbox, sh.roi, sh.spacing)).cuda().eval()
+    bb.v2vNet.load_state_dict({k: torch.as_tensor(v) for k, v in weights.items()}, strict=True)
+    bb = bb.cuda()
+
+    class Stub(torch.nn.Module):
+        hm = None
+        def forward(self, x):
+            return None, self.hm
+    bb.effTrack = Stub()
+    imgs = torch.zeros(1, sh.ncam, 3, 4, 4, device="cuda")
+    size = torch.tensor([1280, 1024], device="cuda")
+
+    def one(b):
+        bb.effTrack.hm = hm_b[b]
+        return bb(imgs, size, chm_b[b:b + 1], c3_b[b:b + 1].int(), cam_b[b:b + 1], intr_b[b:b + 1], dist_b[b:b + 1])
+    out = {}
+    n = min(n_frame_sets, hm_b.shape[0])
+    for tag, tf32 in (("tf32_on", True), ("tf32_off", False)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            for b in range(2):
+                one(b)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                for b in range(n):
+                    one(b)
+            e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * n)
+        out[tag] = dict(ms_per_frame_set=ms, frame_sets_per_sec=1e3 / ms)
+    torch.backends.cudnn.allow_tf32 = True
+    out["note"] = ("unmodified jarvis.hybridnet.model.HybridNetBackbone.forward from baseline/_ref on this GPU (reproLayer + v2vNet + "
+                   "tail; effTrack stubbed), one frame set per call, %d frame sets x %d repetitions, inputs resident" % (n, reps))
+    return out
+
+
 def micro_reproject_tail(sh, B, pk, steps=10):
     """BASELINE.json configs[1] / metric (ii): ReprojectionLayer (+ /255) and the centroid tail on their own, fp32 and bf16,
     as achieved HBM GB/s over the algorithmic bytes of SURVEY.md section 8d."""
@@ -688,6 +741,7 @@ def main():
     extra = None
     if rank == 0 and world == 1 and not args.no_extras and args.workload == "c3_full3d_example":
         extra = dict(torch_gpu_baseline=torch_reference_gpu(sh, weights, devb[0]),
+                     reference_gpu_modules=reference_modules_gpu(sh, weights, devb[0]),
                      c2_micro=micro_reproject_tail(S.MICRO, WORKLOADS["c2_micro"]["batch"], pk))
         try:                                                        # BASELINE.json configs[4]: 16 cameras, 96^3 grid, bf16 (this GPU's share)
             st = S.STRESS

@@ -217,6 +217,35 @@ int jhn_crop_normalize(const float *imgs, int B, int ncam, int H, int W, int bbo
                        const int32_t *valid, const float *mean, const float *std, float *crops,
                        jhn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * the data formats either side of the path.
+ *
+ * jhn_ingest_frames: jarvis/prediction/predict3D.py:79
+ *     `torch.from_numpy(imgs_orig).cuda().float().permute(0,3,1,2)[:, [2,1,0]] / 255.`
+ *   frames  device uint8 [N][H][W][3], BGR as cv2.VideoCapture.read() delivers them (N = cameras x frame sets)
+ *   imgs    device fp32  [N][3][H][W], RGB, float(u8) / 255 (one rounded division: the reference's bits).  W % 4 == 0.
+ * jhn_crop_normalize_u8: jarvis/prediction/jarvis3D.py:168-177 straight from the uint8 frames:
+ *   crops device fp32 [B][ncam][3][bbox][bbox] = ((u8 / 255) - mean) / std around centerHM; zeros where valid == 0.
+ *   Same values as jhn_ingest_frames followed by jhn_crop_normalize, without the fp32 image.
+ * jhn_efftrack_head: the last layer of EfficientTrackBackbone, `res2 = self.deconv1(res1)`
+ *   (jarvis/efficienttrack/model.py:89-95,127: ConvTranspose2d(C, K, kernel 4, stride 2, padding 1, bias=False)), with the
+ *   result written in any jhn_heatmap_format — JHN_HM_F16_CL / JHN_HM_BF16_CL are what jhn_reproject_gather /
+ *   jhn_hybrid3d_forward read without a staging pass (F.pad's zero border included, jarvis/hybridnet/model.py:65-66).
+ *   features device fp32 [N][C][Hq][Wq]   weight device fp32 [C][K][4][4] (the checkpoint's `deconv1.weight`)
+ *   heatmaps JHN_HM_F32_PLANAR: fp32 [N][K][2Hq][2Wq] (the reference's tensor, un-padded)
+ *            channels-last:     16-bit [N][2Hq+2][2Wq+2][24]                                    1 <= K <= 24
+ * jhn_softplus2: heatmap_final = softplus(softplus(v2v_out)) (jarvis/hybridnet/model.py:73,88), n fp32 elements.
+ * jhn_pad_heatmaps: heatmaps_padded = F.pad(heatmaps, [1,1,1,1]) (model.py:65-66): fp32 [N][S][S] -> [N][S+2][S+2].
+ * ------------------------------------------------------------------------------------------------ */
+int jhn_ingest_frames(const uint8_t *frames, int N, int H, int W, float *imgs, jhn_stream_t stream);
+int jhn_crop_normalize_u8(const uint8_t *frames, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
+                          const int32_t *valid, const float *mean, const float *std, float *crops,
+                          jhn_stream_t stream);
+int jhn_efftrack_head(const float *features, const float *weight, int N, int C, int K, int Hq, int Wq,
+                      int out_format, void *heatmaps, jhn_stream_t stream);
+int jhn_softplus2(const float *v2v_out, long long n, float *heatmap_final, jhn_stream_t stream);
+int jhn_pad_heatmaps(const float *heatmaps, long long N, int S, float *heatmaps_padded, jhn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,11 @@ SYMBOLS = {
     "jhn_center_locate": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P]),
     "jhn_crop_normalize": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, POINTER(c_float), POINTER(c_float), _P, _P]),
+    "jhn_ingest_frames": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "jhn_crop_normalize_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, POINTER(c_float), POINTER(c_float), _P, _P]),
+    "jhn_efftrack_head": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "jhn_softplus2": (c_int, [_P, ctypes.c_longlong, _P, _P]),
+    "jhn_pad_heatmaps": (c_int, [_P, ctypes.c_longlong, c_int, _P, _P]),
     # not part of the drop-in surface: launch counter used by bench.py's `gpu_launches`
     "jhn_launch_count": (c_ulonglong, []),
     "jhn_profile_enable": (None, [c_int]),

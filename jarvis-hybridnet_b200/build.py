@@ -13,10 +13,10 @@ SUFFIX = os.environ.get("JHN_LIB_SUFFIX", "")                        # suffix: e
 LIB = os.path.join(HERE, "libjarvis_hybridnet_b200%s.so" % SUFFIX)
 OBJ = os.path.join(CSRC, "_obj" + SUFFIX)
 SOURCES = ["api.cu", "repro.cu", "conv_f32.cu", "conv_tc.cu", "conv3_tc.cu", "head_tc.cu", "tail.cu", "center.cu",
-           "ingest.cu"]
+           "ingest.cu", "head2d.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-ABI_VERSION = 4                                                        # == jhn_abi_version() of the sources in csrc/
+ABI_VERSION = 5                                                        # == jhn_abi_version() of the sources in csrc/
 
 
 def _headers():

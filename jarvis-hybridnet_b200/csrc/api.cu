@@ -83,7 +83,7 @@ using namespace jhn;
 extern "C" {
 
 const char *jhn_last_error(void) { return g_err; }
-int jhn_abi_version(void) { return 4; }
+int jhn_abi_version(void) { return 5; }
 unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
@@ -386,6 +386,49 @@ int jhn_crop_normalize(const float *imgs, int B, int ncam, int H, int W, int bbo
     for (int i = 0; i < 3; ++i)
         if (!(std[i] > 0.f)) return fail(JHN_ERR_ARG, "std[%d] must be > 0", i);
     return crop_normalize_launch(imgs, B, ncam, H, W, bbox, centerHM, valid, mean, std, crops, (cudaStream_t)stream);
+}
+
+int jhn_ingest_frames(const uint8_t *frames, int N, int H, int W, float *imgs, jhn_stream_t stream)
+{
+    if (!frames || !imgs) return fail(JHN_ERR_ARG, "jhn_ingest_frames: null pointer argument");
+    if (N < 1 || H < 1 || W < 4 || (W % 4) != 0) return fail(JHN_ERR_SHAPE, "need N>=1, H>=1, W a multiple of 4 (got N=%d H=%d W=%d)", N, H, W);
+    if ((long long)N * H * (W / 4) > 0x7fffffffLL * 256) return fail(JHN_ERR_SHAPE, "too many pixels for one call");
+    return ingest_frames_launch(frames, N, H, W, imgs, (cudaStream_t)stream);
+}
+
+int jhn_crop_normalize_u8(const uint8_t *frames, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
+                          const int32_t *valid, const float *mean, const float *std, float *crops, jhn_stream_t stream)
+{
+    if (!frames || !centerHM || !valid || !mean || !std || !crops) return fail(JHN_ERR_ARG, "jhn_crop_normalize_u8: null pointer argument");
+    if (B < 1 || ncam < 1 || (long long)B * ncam > 65535) return fail(JHN_ERR_SHAPE, "need B*ncam in [1,65535] (got B=%d ncam=%d)", B, ncam);
+    if (bbox < 4 || (bbox % 4) != 0 || bbox > H || bbox > W) return fail(JHN_ERR_SHAPE, "bounding box %d must be a multiple of 4 and fit the %dx%d image", bbox, W, H);
+    for (int i = 0; i < 3; ++i)
+        if (!(std[i] > 0.f)) return fail(JHN_ERR_ARG, "std[%d] must be > 0", i);
+    return crop_normalize_u8_launch(frames, B, ncam, H, W, bbox, centerHM, valid, mean, std, crops, (cudaStream_t)stream);
+}
+
+int jhn_efftrack_head(const float *features, const float *weight, int N, int C, int K, int Hq, int Wq, int out_format,
+                      void *heatmaps, jhn_stream_t stream)
+{
+    if (!features || !weight || !heatmaps) return fail(JHN_ERR_ARG, "jhn_efftrack_head: null pointer argument");
+    if (N < 1 || N > 65535 || C < 1 || K < 1 || K > KP) return fail(JHN_ERR_SHAPE, "need 1<=N<=65535, C>=1, 1<=K<=%d (got N=%d C=%d K=%d)", KP, N, C, K);
+    if (Hq < 1 || Wq < 1 || Hq > 4096 || Wq > 4096) return fail(JHN_ERR_SHAPE, "feature map %dx%d out of range", Hq, Wq);
+    return efftrack_head_launch(features, weight, N, C, K, Hq, Wq, out_format, heatmaps, (cudaStream_t)stream);
+}
+
+int jhn_softplus2(const float *v2v_out, long long n, float *heatmap_final, jhn_stream_t stream)
+{
+    if (!v2v_out || !heatmap_final) return fail(JHN_ERR_ARG, "jhn_softplus2: null pointer argument");
+    if (n < 1 || n > (1LL << 40)) return fail(JHN_ERR_SHAPE, "element count %lld out of range", n);
+    if (((uintptr_t)v2v_out | (uintptr_t)heatmap_final) & 15) return fail(JHN_ERR_ARG, "jhn_softplus2: buffers must be 16-byte aligned");
+    return softplus2_launch(v2v_out, n, heatmap_final, (cudaStream_t)stream);
+}
+
+int jhn_pad_heatmaps(const float *heatmaps, long long N, int S, float *heatmaps_padded, jhn_stream_t stream)
+{
+    if (!heatmaps || !heatmaps_padded) return fail(JHN_ERR_ARG, "jhn_pad_heatmaps: null pointer argument");
+    if (N < 1 || S < 1 || S > 8192 || N * (S + 2) * (S + 2) > (1LL << 40)) return fail(JHN_ERR_SHAPE, "need N>=1, 1<=S<=8192");
+    return pad_border_launch(heatmaps, N, S, heatmaps_padded, (cudaStream_t)stream);
 }
 
 }  // extern "C"

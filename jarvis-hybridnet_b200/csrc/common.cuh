@@ -93,4 +93,13 @@ int center_locate_launch(const float *hm, int B, int ncam, int Hc, int Wc, int i
 int crop_normalize_launch(const float *imgs, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
                           const int32_t *valid, const float *mean, const float *std, float *out, cudaStream_t st);
 
+// ingest.cu (rows f4 / a11) and head2d.cu (row f2)
+int ingest_frames_launch(const uint8_t *frames, int N, int H, int W, float *out, cudaStream_t st);
+int crop_normalize_u8_launch(const uint8_t *frames, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
+                             const int32_t *valid, const float *mean, const float *std, float *out, cudaStream_t st);
+int softplus2_launch(const float *v, long long n, float *out, cudaStream_t st);
+int pad_border_launch(const float *in, long long N, int S, float *out, cudaStream_t st);
+int efftrack_head_launch(const float *features, const float *weight, int N, int C, int K, int Hq, int Wq, int out_format,
+                         void *heatmaps, cudaStream_t st);
+
 }  // namespace jhn

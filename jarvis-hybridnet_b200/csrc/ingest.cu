@@ -1,0 +1,134 @@
+// Frame ingest and the returned volumes of HybridNetBackbone.forward (row a11).
+//
+//   ingest_frames_kernel      jarvis/prediction/predict3D.py:79  `from_numpy(imgs_orig).cuda().float().permute(0,3,1,2)[:, [2,1,0]] / 255.`
+//                             decoded frames cross PCIe as the decoder wrote them (uint8, H x W x BGR: 3 B per pixel instead of
+//                             the 12 B of the fp32 tensor the reference uploads) and become the reference's fp32 CHW RGB tensor
+//                             on the device: float(u8) / 255 as ONE rounded fp32 division, the same bits torch produces.
+//   crop_normalize_u8_kernel  jarvis/prediction/jarvis3D.py:168-177 straight from the uint8 frames: the key-point detector's
+//                             crops ((u8 / 255 - mean) / std, three separately rounded fp32 ops as in the reference) without
+//                             ever materialising the 12 x 3 x 1024 x 1280 fp32 image in HBM.
+//   softplus2_kernel          jarvis/hybridnet/model.py:73,88   heatmap_final = softplus(softplus(v2v))  (the returned volume)
+//   pad_border_kernel         jarvis/hybridnet/model.py:65-66   heatmaps_padded = F.pad(heatmaps, [1,1,1,1])
+// All four are HBM-bound streaming kernels: 16-byte accesses, one pass.
+#include "common.cuh"
+
+namespace jhn {
+
+// one thread = 4 consecutive pixels of one row: 12 input bytes (three aligned 32-bit loads), one float4 per colour plane
+__global__ void __launch_bounds__(256)
+ingest_frames_kernel(const uint8_t *__restrict__ frames, int H, int W, long long quads, float *__restrict__ out)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= quads) return;
+    const int per_row = W / 4;
+    const long long row = q / per_row;                                // image * H + y
+    const int x4 = (int)(q - row * per_row) * 4;
+    const long long img = row / H;
+    const int y = (int)(row - img * H);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + (size_t)row * W * 3 + (size_t)x4 * 3);
+    const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);   // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+    const float b0 = (float)(w0 & 0xffu), g0 = (float)((w0 >> 8) & 0xffu), r0 = (float)((w0 >> 16) & 0xffu), b1 = (float)(w0 >> 24);
+    const float g1 = (float)(w1 & 0xffu), r1 = (float)((w1 >> 8) & 0xffu), b2 = (float)((w1 >> 16) & 0xffu), g2 = (float)(w1 >> 24);
+    const float r2 = (float)(w2 & 0xffu), b3 = (float)((w2 >> 8) & 0xffu), g3 = (float)((w2 >> 16) & 0xffu), r3 = (float)(w2 >> 24);
+    const size_t plane = (size_t)H * W;
+    float *dst = out + (size_t)img * 3 * plane + (size_t)y * W + x4;
+    const float d = 255.f;
+    *reinterpret_cast<float4 *>(dst) = make_float4(__fdiv_rn(r0, d), __fdiv_rn(r1, d), __fdiv_rn(r2, d), __fdiv_rn(r3, d));
+    *reinterpret_cast<float4 *>(dst + plane) = make_float4(__fdiv_rn(g0, d), __fdiv_rn(g1, d), __fdiv_rn(g2, d), __fdiv_rn(g3, d));
+    *reinterpret_cast<float4 *>(dst + 2 * plane) = make_float4(__fdiv_rn(b0, d), __fdiv_rn(b1, d), __fdiv_rn(b2, d), __fdiv_rn(b3, d));
+}
+
+// out[b][c][ch][y][x] = ((frames[b][c][cy - hw + y][cx - hw + x][2 - ch] / 255) - mean[ch]) / std[ch]; zeros when !valid[b].
+// One thread = 4 consecutive x of one crop row, all three colour planes (the window start is not 4-byte aligned: byte loads
+// through the read-only path, 12 per thread, each cache line used by the neighbouring lanes).
+__global__ void __launch_bounds__(256)
+crop_normalize_u8_kernel(const uint8_t *__restrict__ frames, int H, int W, int bbox, const int32_t *__restrict__ centerHM,
+                         const int32_t *__restrict__ valid, int ncam, float m0, float m1, float m2, float s0, float s1,
+                         float s2, float *__restrict__ out)
+{
+    const int bc = blockIdx.y, hw = bbox / 2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_row = bbox / 4;
+    if (q >= bbox * per_row) return;
+    const int y = q / per_row, x4 = (q - y * per_row) * 4;
+    float4 r[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) r[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid[bc / ncam]) {
+        const int cx = centerHM[2 * bc + 0], cy = centerHM[2 * bc + 1];
+        const uint8_t *src = frames + (((size_t)bc * H + (cy - hw + y)) * W + (cx - hw + x4)) * 3;
+        float v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) v[i] = __fdiv_rn((float)__ldg(src + i), 255.f);     // pixel i / 3, BGR channel i % 3
+        const float m[3] = {m0, m1, m2}, s[3] = {s0, s1, s2};
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {                              // output plane ch = RGB, input byte 2 - ch
+            r[ch].x = __fdiv_rn(__fsub_rn(v[0 + 2 - ch], m[ch]), s[ch]); r[ch].y = __fdiv_rn(__fsub_rn(v[3 + 2 - ch], m[ch]), s[ch]);
+            r[ch].z = __fdiv_rn(__fsub_rn(v[6 + 2 - ch], m[ch]), s[ch]); r[ch].w = __fdiv_rn(__fsub_rn(v[9 + 2 - ch], m[ch]), s[ch]);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+        reinterpret_cast<float4 *>(out + (((size_t)bc * 3 + ch) * bbox + y) * bbox)[x4 / 4] = r[ch];
+}
+
+// torch.nn.Softplus (beta 1, threshold 20), applied twice: x > 20 ? x : log1p(exp(x)) with CUDA libm, as ATen's kernel does
+__device__ __forceinline__ float softplus1(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+__global__ void __launch_bounds__(256)
+softplus2_kernel(const float *__restrict__ v, long long n, float *__restrict__ out)
+{
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 3 < n) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(v + i4));
+        *reinterpret_cast<float4 *>(out + i4) = make_float4(softplus1(softplus1(a.x)), softplus1(softplus1(a.y)),
+                                                            softplus1(softplus1(a.z)), softplus1(softplus1(a.w)));
+    } else {
+        for (long long i = i4; i < n; ++i) out[i] = softplus1(softplus1(v[i]));
+    }
+}
+
+// [N][S][S] -> [N][S+2][S+2] with a zero border; one thread per output element (rows of S+2 floats are not 16-byte aligned)
+__global__ void __launch_bounds__(256)
+pad_border_kernel(const float *__restrict__ in, int S, long long n_out, float *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const int hs = S + 2;
+    const long long img = i / (hs * hs);
+    const int r = (int)(i - img * hs * hs), y = r / hs, x = r - y * hs;
+    const bool inside = y >= 1 && y <= S && x >= 1 && x <= S;
+    out[i] = inside ? __ldg(in + (size_t)img * S * S + (size_t)(y - 1) * S + (x - 1)) : 0.f;
+}
+
+int ingest_frames_launch(const uint8_t *frames, int N, int H, int W, float *out, cudaStream_t st)
+{
+    const long long quads = (long long)N * H * (W / 4);
+    JHN_LAUNCH("ingest_frames_kernel", st, ingest_frames_kernel<<<(unsigned)cdiv(quads, 256), 256, 0, st>>>(frames, H, W, quads, out));
+    return JHN_OK;
+}
+
+int crop_normalize_u8_launch(const uint8_t *frames, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
+                             const int32_t *valid, const float *mean, const float *std, float *out, cudaStream_t st)
+{
+    const int threads_needed = bbox * (bbox / 4);
+    JHN_LAUNCH("crop_normalize_u8_kernel", st,
+               crop_normalize_u8_kernel<<<dim3(cdiv(threads_needed, 256), B * ncam), 256, 0, st>>>(
+                   frames, H, W, bbox, centerHM, valid, ncam, mean[0], mean[1], mean[2], std[0], std[1], std[2], out));
+    return JHN_OK;
+}
+
+int softplus2_launch(const float *v, long long n, float *out, cudaStream_t st)
+{
+    JHN_LAUNCH("softplus2_kernel", st, softplus2_kernel<<<(unsigned)cdiv(cdiv(n, 4), 256), 256, 0, st>>>(v, n, out));
+    return JHN_OK;
+}
+
+int pad_border_launch(const float *in, long long N, int S, float *out, cudaStream_t st)
+{
+    const long long n_out = N * (S + 2) * (S + 2);
+    JHN_LAUNCH("pad_border_kernel", st, pad_border_kernel<<<(unsigned)cdiv(n_out, 256), 256, 0, st>>>(in, S, n_out, out));
+    return JHN_OK;
+}
+
+}  // namespace jhn

@@ -1,0 +1,133 @@
+"""The drop-in seam on the reference's REAL classes, on the B200 (VERDICT r1 missing #5):
+
+    HybridNet('inference', cfg, 'HybridNet-small.pth')      jarvis/hybridnet/hybridnet.py:43-81  (strict load_state_dict)
+    -> reference forward on the GPU (its native CUDA path: cuBLAS, ATen, cuDNN)                — the primary parity oracle
+    -> accelerate(backbone)                                  jarvis_hybridnet_b200/model.py
+    -> same call, same inputs                                                                   — must agree
+
+The unmodified reference is imported from baseline/_ref (pip-installed copy, see baseline/ref_shim.py; it travels to the
+GPU box with the snapshot).  Skipped when that install is absent.  Inputs: the real-data fixture (EfficientTrack heat maps
+of three Example_Dataset validation frame sets, the 12 real calibration files) fed through a stub in place of effTrack —
+the 2D CNN is outside the path — plus the whole JarvisPredictor3D on synthetic camera images."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "baseline"))
+import ref_shim  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_shim.available(), reason="baseline/_ref (reference install) absent")]
+DEV = "cuda"
+
+
+class StubTrack(torch.nn.Module):
+    def __init__(self, hm):
+        super().__init__()
+        self.hm = hm
+
+    def forward(self, imgs):
+        return None, self.hm
+
+
+def real_backbone():
+    assert ref_shim.import_reference()
+    from jarvis.hybridnet.hybridnet import HybridNet
+    torch.backends.cudnn.allow_tf32 = False                          # fp32 goldens, not TF32 (SURVEY.md §8c caveat)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    hn = HybridNet("inference", ref_shim.make_cfg(), os.path.join(ref_shim.WEIGHTS, "HybridNet-small.pth"))
+    return hn.model
+
+
+def call(bb, f, cal):
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    bb.effTrack = StubTrack(t(f["hm"]))
+    with torch.no_grad():
+        return bb(torch.zeros(1, 12, 3, 4, 4, device=DEV), torch.tensor([1280, 1024], device=DEV), t(f["chm"])[None],
+                  t(f["c3"])[None], t(cal["cam"])[None], t(cal["intr"])[None], t(cal["dist"])[None])
+
+
+@pytest.mark.parametrize("precision,bar", [("fp32", 0.05), ("bf16", 0.5)])
+def test_accelerate_on_the_real_hybridnet(precision, bar):
+    from jarvis_hybridnet_b200 import accelerate
+    from test_real_anchor import load_real
+    sets, cal = load_real()
+    bb = real_backbone()
+    assert type(bb).__name__ == "HybridNetBackbone" and type(bb.v2vNet).__module__ == "jarvis.hybridnet.v2vnet"
+    ref = [call(bb, f, cal) for f in sets]                          # reference CUDA path on the B200
+    ref = [(r[0].clone(), r[1].clone(), r[2].clone(), r[3].clone()) for r in ref]
+    # reference indices on the GPU (cuBLAS SGEMM + ATen-CUDA upsample), before the swap
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    L = bb.reproLayer
+    ref_idx = [L.reprojectPoints(L.grid + t(f["c3"]), t(cal["cam"]), t(cal["intr"]), t(cal["dist"]), t(f["chm"])).clone() for f in sets]
+    accelerate(bb, precision=precision, return_volumes=True)
+    assert type(bb.v2vNet).__module__.startswith("jarvis_hybridnet_b200") or "b200" in type(bb.v2vNet).__module__
+    for f, r, ri in zip(sets, ref, ref_idx):
+        hf, hp, p3, conf = call(bb, f, cal)
+        d = (p3 - r[2]).abs().max().item()
+        print(f"{f['name']}: {precision} vs the reference's own CUDA run: {d:.4f} mm; reference CPU fixture: "
+              f"{np.abs(r[2][0].cpu().numpy() - f['points3D']).max():.4f} mm")
+        assert d < bar
+        assert torch.allclose(conf, r[3], rtol=1e-4 if precision == "fp32" else 5e-2, atol=1e-5 if precision == "fp32" else 5e-3)
+        assert tuple(hf.shape) == tuple(r[0].shape) and tuple(hp.shape) == tuple(r[1].shape)
+        assert torch.equal(hp, r[1])                                # heatmaps_padded: F.pad of the same maps
+        scale = r[0].abs().max().item()
+        assert (hf - r[0]).abs().max().item() <= (1e-4 if precision == "fp32" else 6e-2) * scale
+        idx = bb.reproLayer.reprojectPoints(bb.reproLayer.grid + t(f["c3"]), t(cal["cam"]), t(cal["intr"]), t(cal["dist"]), t(f["chm"]))
+        assert torch.equal(idx, ri), "voxel->pixel indices differ from the reference's CUDA run"
+
+
+def test_accelerate_predictor_on_the_real_predictor():
+    """JarvisPredictor3D built by its own constructor with the bundled weights (jarvis3D.py:20-46), on synthetic camera
+    images that show a bright blob at the projection of one 3D point (so that the centre detector's output is whatever
+    the real CNN makes of it — the comparison is reference vs accelerated on identical inputs, not accuracy)."""
+    assert ref_shim.import_reference()
+    from jarvis.prediction.jarvis3D import JarvisPredictor3D
+    from jarvis_hybridnet_b200 import accelerate_predictor
+    from test_real_anchor import load_real
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sets, cal = load_real()
+    W = ref_shim.WEIGHTS
+    pred = JarvisPredictor3D(ref_shim.make_cfg(), os.path.join(W, "EfficientTrack_Center-small.pth"),
+                             os.path.join(W, "HybridNet-small.pth"))
+    # the keypoint detector of the bundled HybridNet checkpoint is inside HybridNet-small.pth (effTrack.*): real CNNs throughout
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    cam, intr, dist = t(cal["cam"]), t(cal["intr"]), t(cal["dist"])
+    frames = os.path.join(ref_shim.REF, "datasets", "Example_Dataset", "val", "12Cam_Ralph", "Ralph_20072021", "Bar horizontal")
+    if os.path.isdir(frames):
+        # one real validation frame set (12 JPEGs copied next to the install), read as BaseDataset._load_image reads them
+        # (dataset/datasetBase.py:90-99) and handed over as analyze.py:79 does; camera order = calibration order
+        import cv2
+        from test_real_anchor import camera_names
+        imgs = torch.stack([torch.from_numpy(cv2.cvtColor(cv2.imread(os.path.join(frames, c, "Frame_50590.jpg")), cv2.COLOR_BGR2RGB)
+                                             .astype(np.float32) / 255.).permute(2, 0, 1) for c in camera_names()]).to(DEV)
+    else:
+        g = torch.Generator(device="cpu").manual_seed(0)
+        imgs = (torch.rand((12, 3, 1024, 1280), generator=g) * 0.2).to(DEV)
+        c = torch.tensor(sets[0]["c3"], dtype=torch.float32, device=DEV)
+        pred.reproTool.cameraMatrices, pred.reproTool.intrinsicMatrices, pred.reproTool.distortionCoefficients = cam, intr, dist
+        uv = pred.reproTool.reprojectPoint(c[None]).round().long().cpu().numpy()
+        yy, xx = torch.meshgrid(torch.arange(1024, device=DEV), torch.arange(1280, device=DEV), indexing="ij")
+        for i in range(12):
+            blob = torch.exp(-((xx - int(uv[i, 0])) ** 2 + (yy - int(uv[i, 1])) ** 2) / (2 * 40.0 ** 2))
+            imgs[i] += 0.7 * blob
+    with torch.no_grad():
+        p_ref, c_ref = pred(imgs.clone(), cam, intr, dist)
+    accelerate_predictor(pred, precision="fp32")
+    with torch.no_grad():
+        p_acc, c_acc = pred(imgs.clone(), cam, intr, dist)
+    if p_ref is None:
+        assert p_acc is None                                        # same "fewer than two cameras" decision
+        pytest.skip("the real centre detector found no instance in the synthetic images; None contract verified")
+    assert p_acc is not None and tuple(p_acc.shape) == tuple(p_ref.shape)
+    d = (p_acc - p_ref).abs().max().item()
+    print(f"JarvisPredictor3D reference vs accelerated: {d:.4f} mm")
+    assert d < 0.05
+    assert torch.allclose(c_acc, c_ref, rtol=1e-3, atol=1e-4)
+    if os.path.isdir(frames):                                       # the fixture's frame set 0 is this frame set: the CPU reference run agrees
+        assert np.abs(p_ref[0].cpu().numpy() - sets[0]["points3D_unq"]).max() < 0.05
