@@ -10,7 +10,9 @@ def __getattr__(name):
     table = {"ReprojectionLayer": "repro_layer", "V2VNet": "v2vnet", "HybridNet3D": "model", "accelerate": "model",
              "centroid_tail": "model", "shard_range": "model", "gather_results": "model",
              "write_data3D_csv": "output", "create_info_file": "output",
-             "locate_center": "predictor", "crop_normalize": "predictor", "accelerate_predictor": "predictor"}
+             "locate_center": "predictor", "crop_normalize": "predictor", "accelerate_predictor": "predictor",
+             "predict3D_frames": "predictor", "ingest_frames": "ingest", "crop_normalize_u8": "ingest", "EffTrackHead": "ingest",
+             "FrameUploader": "ingest", "softplus2": "ingest", "pad_heatmaps": "ingest", "format_rows": "output"}
     if name in table:
         return getattr(importlib.import_module("." + table[name], __name__), name)
     raise AttributeError(name)

@@ -14,7 +14,6 @@ import types
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib
 from .repro_layer import ReprojectionLayer
@@ -40,9 +39,12 @@ def centroid_tail(v2v_out, spacing, roi, center3D, want_argmax=False):
 def _accelerated_forward(self, imgs, img_size, centerHM, center3D, cameraMatrices, intrinsicMatrices,
                          distortionCoefficients):
     """Replacement for HybridNetBackbone.forward with the same signature and return tuple (model.py:53-90).
-    effTrack is still the reference module (out of scope); everything after it runs on the B200 kernels.
-    `heatmap_final` / `heatmaps_padded` are only materialised when `self.return_volumes` is True: every
-    inference caller discards them (jarvis3D.py:180)."""
+    effTrack is still the reference module (out of scope) — with `accelerate(head_format=...)` its last layer writes the
+    gather's channels-last layout (row f2) — and everything after it runs on the B200 kernels.  Like the reference
+    (`center[0]`, `centerHM[0]`, repro_layer.py:109-119) one call serves ONE frame set; `forward_batched` serves B.
+    `heatmap_final` / `heatmaps_padded` are only materialised when `self.return_volumes` is True: every inference caller
+    discards them (jarvis3D.py:180)."""
+    from .ingest import pad_heatmaps, softplus2
     batch_size = imgs.shape[0]
     self.heatmap_size = (img_size / 2).int()
     hm = self.effTrack(imgs.reshape(-1, imgs.shape[2], imgs.shape[3], imgs.shape[4]))[1]
@@ -54,14 +56,31 @@ def _accelerated_forward(self, imgs, img_size, centerHM, center3D, cameraMatrice
     points3D, confidences = centroid_tail(v, float(self.grid_spacing), float(self.grid_size), center3D[:1])
     heatmap_final = heatmaps_padded = None
     if getattr(self, "return_volumes", False):
-        heatmap_final = F.softplus(F.softplus(v))                                  # model.py:73,88
-        heatmaps_padded = F.pad(hm, [1, 1, 1, 1])                                  # model.py:65-66
+        if hm.dtype != torch.float32:
+            raise RuntimeError("return_volumes needs the planar fp32 heat maps: use accelerate(..., head_format=None)")
+        heatmap_final = softplus2(v)                                               # model.py:73,88 (jhn_softplus2)
+        heatmaps_padded = pad_heatmaps(hm)                                         # model.py:65-66 (jhn_pad_heatmaps)
     return heatmap_final, heatmaps_padded, points3D, confidences
 
 
-def accelerate(backbone, precision="fp32", lerp_mode=_lib.LERP_FMA_FIRST, return_volumes=False):
+def _forward_batched(self, imgs, img_size, centerHM, center3D, cameraMatrices, intrinsicMatrices, distortionCoefficients):
+    """B frame sets per call — what the reference's forward leaves as a TODO (model.py:75): crops [B,ncam,3,bb,bb],
+    centerHM [B,ncam,2], center3D [B,3], calibration [B,ncam,...] or un-batched [ncam,...] (shared rig) ->
+    points3D [B,K,3], confidences [B,K].  The 3D stages run through ONE jhn_hybrid3d_forward call."""
+    B = imgs.shape[0]
+    hm = self.effTrack(imgs.reshape(-1, imgs.shape[2], imgs.shape[3], imgs.shape[4]))[1]
+    hm = hm.reshape(B, -1, hm.shape[1], hm.shape[2], hm.shape[3])
+    ex = lambda t, nd: t if t.dim() == nd else t[None].expand(B, *t.shape)
+    pts, conf, _ = self._jhn3d(hm, center3D, centerHM, ex(cameraMatrices, 4), ex(intrinsicMatrices, 4),
+                               ex(distortionCoefficients, 4))
+    return pts, conf
+
+
+def accelerate(backbone, precision="fp32", lerp_mode=_lib.LERP_FMA_FIRST, return_volumes=False, head_format=None):
     """Swap the 3D stages of a reference HybridNetBackbone (already built and `load_state_dict`-ed by
-    jarvis.hybridnet.hybridnet.HybridNet, hybridnet.py:77-90) for the B200 implementation, in place."""
+    jarvis.hybridnet.hybridnet.HybridNet, hybridnet.py:77-90) for the B200 implementation, in place.
+    head_format "f16_cl" / "bf16_cl" (bf16 precision) also swaps `effTrack.deconv1` for ingest.EffTrackHead so that the
+    2D network emits the gather's layout directly; None keeps the reference layer."""
     cfg = backbone.cfg
     K = cfg.KEYPOINTDETECT.NUM_JOINTS
     new_v2v = V2VNet(K, K, precision=precision)
@@ -70,8 +89,17 @@ def accelerate(backbone, precision="fp32", lerp_mode=_lib.LERP_FMA_FIRST, return
     backbone.v2vNet = new_v2v.to(dev)
     backbone.reproLayer = ReprojectionLayer(cfg, getattr(backbone.reproLayer, "num_cameras", None),
                                             precision=precision, lerp_mode=lerp_mode)
+    if head_format is not None:
+        if precision != "bf16":
+            raise RuntimeError("channels-last 16-bit heat maps belong to the bf16 path")
+        from .ingest import EffTrackHead
+        backbone.effTrack.deconv1 = EffTrackHead.from_deconv(backbone.effTrack.deconv1, head_format)
     backbone.return_volumes = return_volumes
+    h3d = HybridNet3D(K, cfg.KEYPOINTDETECT.BOUNDING_BOX_SIZE, cfg.HYBRIDNET.ROI_CUBE_SIZE, cfg.HYBRIDNET.GRID_SPACING,
+                      precision=precision, lerp_mode=lerp_mode, v2vNet=backbone.v2vNet)
+    object.__setattr__(backbone, "_jhn3d", h3d)                  # not a registered sub-module: the state_dict keeps the reference's keys
     backbone.forward = types.MethodType(_accelerated_forward, backbone)
+    backbone.forward_batched = types.MethodType(_forward_batched, backbone)
     return backbone
 
 
@@ -82,13 +110,13 @@ class HybridNet3D(nn.Module):
             centerHM [B,ncam,2] i32, cameraMatrices [B,ncam,4,3], intrinsicMatrices [B,ncam,3,3],
             distortionCoefficients [B,ncam,1,5]) -> points3D [B,K,3] mm, confidences [B,K], argmax [B,K]"""
 
-    def __init__(self, K, bbox, roi, spacing, state_dict=None, precision="bf16", lerp_mode=_lib.LERP_FMA_FIRST):
+    def __init__(self, K, bbox, roi, spacing, state_dict=None, precision="bf16", lerp_mode=_lib.LERP_FMA_FIRST, v2vNet=None):
         super().__init__()
         self.K, self.roi, self.spacing = K, roi, spacing
         self.G = int(roi / spacing)
         self.hs = int(bbox / 2 + 2)
         self.lerp_mode = lerp_mode
-        self.v2vNet = V2VNet(K, K, precision=precision)
+        self.v2vNet = V2VNet(K, K, precision=precision) if v2vNet is None else v2vNet     # v2vNet: share a loaded network
         if state_dict is not None:
             sd = {k[len("v2vNet."):] if k.startswith("v2vNet.") else k: torch.as_tensor(v) for k, v in state_dict.items()}
             self.v2vNet.load_state_dict(sd, strict=True)

@@ -131,3 +131,66 @@ def test_accelerate_predictor_on_the_real_predictor():
     assert torch.allclose(c_acc, c_ref, rtol=1e-3, atol=1e-4)
     if os.path.isdir(frames):                                       # the fixture's frame set 0 is this frame set: the CPU reference run agrees
         assert np.abs(p_ref[0].cpu().numpy() - sets[0]["points3D_unq"]).max() < 0.05
+
+
+def test_predict_frames_batched_on_the_real_predictor(tmp_path):
+    """The batched entry (predictor.predict_frames / predict3D_frames, rows f4 + f1 + f2 + f3 around the 3D path) on the
+    reference's real JarvisPredictor3D with one real validation frame set: every frame set of a batch must reproduce what
+    the reference's own forward returns for it (fp32: 0.05 mm; bf16 + channels-last head: 0.5 mm), and the CSV rows must be
+    the reference loop's bytes for those values."""
+    import cv2
+    assert ref_shim.import_reference()
+    from jarvis.prediction.jarvis3D import JarvisPredictor3D
+    from jarvis_hybridnet_b200 import accelerate_predictor
+    from jarvis_hybridnet_b200.predictor import predict3D_frames
+    from test_real_anchor import camera_names, load_real
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    frames = os.path.join(ref_shim.REF, "datasets", "Example_Dataset", "val", "12Cam_Ralph", "Ralph_20072021", "Bar horizontal")
+    if not os.path.isdir(frames):
+        pytest.skip("real validation frames absent from baseline/_ref")
+    sets, cal = load_real()
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+    cam, intr, dist = t(cal["cam"]), t(cal["intr"]), t(cal["dist"])
+    bgr = np.stack([cv2.imread(os.path.join(frames, c, "Frame_50590.jpg")) for c in camera_names()])     # [12,1024,1280,3] u8
+    dark = (bgr // 8).astype(np.uint8)                               # a frame set the centre detector does not fire on
+    W = ref_shim.WEIGHTS
+    mk = lambda: JarvisPredictor3D(ref_shim.make_cfg(), os.path.join(W, "EfficientTrack_Center-small.pth"), os.path.join(W, "HybridNet-small.pth"))
+    pred = mk()
+    ref = []
+    with torch.no_grad():
+        for fr in (bgr, dark, bgr[:, ::-1, ::-1].copy()):
+            imgs = torch.from_numpy(fr).cuda().float().permute(0, 3, 1, 2)[:, [2, 1, 0]] / 255.             # predict3D.py:79
+            p, c = pred(imgs, cam, intr, dist)
+            ref.append(None if p is None else (p.clone(), c.clone()))
+    assert ref[0] is not None
+    batch = torch.from_numpy(np.stack([bgr, dark, bgr[:, ::-1, ::-1].copy()])).to(DEV)
+    for precision, head, bar in (("fp32", None, 0.05), ("bf16", "f16_cl", 0.5)):
+        acc = accelerate_predictor(mk(), precision=precision, head_format=head)
+        with torch.no_grad():
+            pts, conf, valid = acc.predict_frames(batch, cam, intr, dist)
+        for i, r in enumerate(ref):
+            assert bool(valid[i].item()) == (r is not None)
+            if r is not None:
+                dmax = (pts[i] - r[0][0]).abs().max().item()
+                print(f"predict_frames[{i}] {precision}/{head}: {dmax:.4f} mm vs the reference predictor")
+                assert dmax < bar
+                assert torch.allclose(conf[i], r[1][0], rtol=1e-3 if precision == "fp32" else 5e-2, atol=1e-4 if precision == "fp32" else 5e-3)
+        if precision == "fp32":
+            # the predict3D loop (decode -> pinned -> upload -> batches of 2 -> rows): 5 frame sets cycling through the three
+            seq = [bgr, dark, bgr[:, ::-1, ::-1], bgr, dark]
+            it = iter(seq)
+
+            def read(dst):
+                fr = next(it, None)
+                if fr is None:
+                    return False
+                dst[...] = fr
+                return True
+            path = str(tmp_path / "data3D.csv")
+            n = predict3D_frames(acc, read, 5, (cam, intr, dist), path, 12, (1280, 1024), batch=2)
+            assert n == 5
+            rows = open(path).read().splitlines()
+            assert len(rows) == 5 and rows[1] == ",".join(["NaN"] * 92) and rows[4] == rows[1] and rows[0] == rows[3]
+            vals = np.array([float(v) for v in rows[0].split(",")], np.float64).reshape(23, 4)
+            assert np.abs(vals[:, :3] - ref[0][0][0].cpu().numpy()).max() < 0.05
