@@ -24,12 +24,7 @@
 //     warps 2-9   epilogue: two warps per TMEM lane quadrant, each owning half of the output channels:
 //                 tcgen05.ld -> shuffle-combine -> bias -> pad mask -> bf16 store, and the per-channel
 //                 sum / sum-of-squares of the following InstanceNorm accumulated in registers across tiles
-//                 (written to the CTA's own slot when its range leaves a sample: deterministic, tc_ptx.cuh).
-//     NORM_IN: 4 transform warps.  The input tensor is then the RAW output of the previous convolution and the
-//                 InstanceNorm + ReLU between the two (v2vnet.py:18-19,33-34,54-55) is applied to each plane box in shared
-//                 memory between the bulk copy and the MMAs — (x - mean) * rstd, ReLU, bf16, the same arithmetic as
-//                 tc_norm_act_kernel — so the normalised tensor never exists in HBM (one full read + write pass of the
-//                 activation tensor less per fused layer).  Pad positions stay zero (mask), pad planes are skipped.
+//                 (one atomicAdd per channel and warp when the CTA's range leaves a sample).
 #include "tc_ptx.cuh"
 #include "v2v.cuh"
 
@@ -50,8 +45,6 @@ struct C3Launch {
     int B, D, NT, total_tiles;
     int NS, PB;                                        // ring slots, positions per plane box
     int add_bias;                                      // 0 when an InstanceNorm follows (it cancels the bias exactly)
-    StatPart in_stats;                                 // NORM_IN: statistics of the raw input tensor (slots of its producer)
-    float in_inv_count, in_eps;
 };
 
 // one 8-column piece of the three dx groups, loaded and waited for in ONE asm statement so that no consumer of
@@ -71,16 +64,11 @@ __device__ __forceinline__ void c3_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, 
 }
 
 // EW = epilogue warps per TMEM lane quadrant; each owns NOUT / EW output channels
-// Transform warps of the NORM_IN variant.  Two, not four: registers are per SM sub-partition (16 K each, warp w on
-// sub-partition w % 4), so 16 warps keep the 128 registers per thread the epilogue needs, while an 18-warp CTA would be
-// cut to 96 (five warps on two of the sub-partitions) whatever setmaxnreg does afterwards.
-constexpr int C3_XF_THREADS = 64;
-
-template <int NOUT, int EW, bool NORM_IN>
-__global__ void __launch_bounds__(64 + 128 * EW + (NORM_IN ? C3_XF_THREADS : 0), 1)
+template <int NOUT, int EW>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
 tc_conv3_kernel(const C3Launch L)
 {
-    constexpr int C3_THREADS = 64 + 128 * EW + (NORM_IN ? C3_XF_THREADS : 0);
+    constexpr int C3_THREADS = 64 + 128 * EW;
     constexpr int KC = NOUT / 8;                       // 8-channel chunks of the input (Cin == Cout == NOUT)
     constexpr int N3 = 3 * NOUT;                       // MMA N: three x-taps stacked
     constexpr int CW = NOUT / EW;                      // output channels per epilogue warp
@@ -99,15 +87,13 @@ tc_conv3_kernel(const C3Launch L)
     float *bias_s = xch + 2 * 4 * 2 * NOUT;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + NOUT);
     uint64_t *full = bars, *empty = bars + C3_MAX_SLOTS, *tfull = bars + 2 * C3_MAX_SLOTS, *tempty = tfull + 2, *wbar = tempty + 2;
-    uint64_t *xfull = wbar + 1;                                                   // [C3_MAX_SLOTS] box normalised (NORM_IN)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xfull + C3_MAX_SLOTS);
-    float *ntab = reinterpret_cast<float *>(tmem_slot + 2);                       // [NOUT][mean, rstd] of the current sample (NORM_IN)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wbar + 1);
 
     const int t_begin = (int)((long long)L.total_tiles * blockIdx.x / gridDim.x);
     const int t_end = (int)((long long)L.total_tiles * (blockIdx.x + 1) / gridDim.x);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < L.NS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); mbar_init(smem_u32(xfull + i), C3_XF_THREADS / 32); }
+        for (int i = 0; i < L.NS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * EW); }
         mbar_init(smem_u32(wbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -159,7 +145,6 @@ tc_conv3_kernel(const C3Launch L)
         }
     } else if (warp == 1) {
         // =================================== MMA issuer ======================================
-        uint64_t *ready = NORM_IN ? xfull : full;                              // what an MMA waits for: box landed / box normalised
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(N3);
             const uint64_t hi_c = (uint64_t)(8u | (1u << 14)) << 32;           // SBO = 128 B, descriptor version 1
@@ -182,7 +167,7 @@ tc_conv3_kernel(const C3Launch L)
                 for (int dz = 0; dz < 3; ++dz) {
                     const int i = k - 3 + dz, slot = i % L.NS;
                     if (fresh || dz == 2) {
-                        mbar_wait(smem_u32(ready + slot), (uint32_t)(i / L.NS) & 1u);
+                        mbar_wait(smem_u32(full + slot), (uint32_t)(i / L.NS) & 1u);
                         tc_fence_after();
                     }
                     const uint32_t a0 = ring_units + (uint32_t)slot * slot_units;
@@ -204,88 +189,6 @@ tc_conv3_kernel(const C3Launch L)
                 if (++ab == 2) { ab = 0; aphase ^= 1; }
                 if (++z == D) z = 0;
             }
-        }
-    } else if (NORM_IN && warp >= 2 + 4 * EW) {
-        // =================================== transform warps (NORM_IN) ======================
-        // Thread = (8-channel chunk j, position lane l): it keeps the chunk's 8 (mean, rstd) pairs of the current sample in
-        // registers and walks positions l, l + TPC, ... of every plane box in the order the producer loads them.
-        constexpr int TPC = C3_XF_THREADS / KC;                                // threads per chunk
-        const int tid = (int)threadIdx.x - 32 * (2 + 4 * EW);
-        const int j = tid / TPC, l = tid - j * TPC;
-        const bool active = j < KC;
-        const int NI = (L.PB + TPC - 1) / TPC;                                 // positions per thread and box (<= 64 - 4)
-        uint64_t sc2[4], sh2[4];                                               // (scale, scale), (shift, shift) pairs of the chunk's 8 channels
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { sc2[i] = 0ull; sh2[i] = 0ull; }
-        int cur_b = -1;
-        uint64_t padbits = 0;                                                  // bit i: position l + TPC * i of this column's box is padding (stays zero)
-        int slot = 0; uint32_t phase = 0;
-        int z = t_begin % D, u = t_begin / D;
-        for (int t = t_begin; t < t_end; ++t) {
-            const int pt = u % L.NT, b = u / L.NT;
-            const bool fresh = (t == t_begin) || (z == 0);
-            if (b != cur_b) {
-                // second stage of the producer's statistics for sample b: its per-CTA slots added in slot order in fp64
-                cur_b = b;
-                asm volatile("bar.sync 8, %0;" ::"n"(C3_XF_THREADS) : "memory");
-                for (int ch = tid; ch < NOUT; ch += C3_XF_THREADS) {
-                    const StatPart &S = L.in_stats;
-                    const int c0 = stat_owner((long long)b * S.Tb, S.grid, S.T);
-                    const int c1 = stat_owner((long long)(b + 1) * S.Tb - 1, S.grid, S.T);
-                    const int nslots = (c1 - c0 + 1) * 4;
-                    const float2 *src = reinterpret_cast<const float2 *>(S.part) + (size_t)(c0 + b) * 4 * NOUT + ch;
-                    double s1 = 0.0, s2 = 0.0;
-#pragma unroll 4
-                    for (int s = 0; s < nslots; ++s) { const float2 v = __ldg(src + (size_t)s * NOUT); s1 += (double)v.x; s2 += (double)v.y; }
-                    const double m = s1 * (double)L.in_inv_count;
-                    const double var = fmax(s2 * (double)L.in_inv_count - m * m, 0.0);
-                    const float2 ss = norm_scale_shift((float)m, (float)(1.0 / sqrt(var + (double)L.in_eps)));
-                    ntab[2 * ch] = ss.x;
-                    ntab[2 * ch + 1] = ss.y;
-                }
-                asm volatile("bar.sync 8, %0;" ::"n"(C3_XF_THREADS) : "memory");
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        sc2[i] = f2_pack(ntab[2 * (8 * j + 2 * i)], ntab[2 * (8 * j + 2 * i + 1)]);
-                        sh2[i] = f2_pack(ntab[2 * (8 * j + 2 * i) + 1], ntab[2 * (8 * j + 2 * i + 1) + 1]);
-                    }
-                }
-            }
-            if (fresh) {
-                const int start = C3_VALID * pt, npos = min(L.PB, PP - start);
-                padbits = 0;
-                for (int i = 0; i < NI; ++i) {
-                    const int pp = l + TPC * i, p = start + pp;
-                    const int yp = p / Wp, xp = p - yp * Wp;
-                    if (pp < npos && !(xp >= 1 && xp <= D && yp >= 1 && yp <= D)) padbits |= 1ull << i;
-                }
-            }
-            for (int dz = fresh ? 0 : 2; dz < 3; ++dz) {
-                mbar_wait(smem_u32(full + slot), phase);
-                const int zin = z + dz;                                        // padded plane index: 0 and D + 1 are the zero planes
-                if (active && zin >= 1 && zin <= D) {
-                    uint4 *box = reinterpret_cast<uint4 *>(ring + (size_t)slot * slot_bytes) + (size_t)j * L.PB + l;
-                    // every position of the box, no mask in the loop: the few pad positions are put back to zero afterwards
-#pragma unroll 4
-                    for (int i = 0; i < NI; ++i) {
-                        const bool in = l + TPC * i < L.PB;
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        if (in) v = box[i * TPC];
-                        v.x = norm_relu_bf16x2(v.x, sc2[0], sh2[0]);
-                        v.y = norm_relu_bf16x2(v.y, sc2[1], sh2[1]);
-                        v.z = norm_relu_bf16x2(v.z, sc2[2], sh2[2]);
-                        v.w = norm_relu_bf16x2(v.w, sc2[3], sh2[3]);
-                        if (in) box[i * TPC] = v;
-                    }
-                    for (uint64_t bad = padbits; bad; bad &= bad - 1) box[(__ffsll((long long)bad) - 1) * TPC] = make_uint4(0, 0, 0, 0);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's operand reads
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(xfull + slot));
-                if (++slot == L.NS) { slot = 0; phase ^= 1; }
-            }
-            if (++z == D) { z = 0; ++u; }
         }
     } else {
         // =================================== epilogue warps =================================
@@ -433,7 +336,7 @@ __global__ void c3_pack_weights_kernel(const float *__restrict__ src, __nv_bfloa
     dst[e] = __float2bfloat16_rn(v);
 }
 
-static size_t c3_tail_bytes(int NOUT) { return (size_t)(2 * 4 * 2 * NOUT + NOUT) * 4 + (3 * C3_MAX_SLOTS + 5) * 8 + 16 + (size_t)2 * NOUT * 4; }
+static size_t c3_tail_bytes(int NOUT) { return (size_t)(2 * 4 * 2 * NOUT + NOUT) * 4 + (2 * C3_MAX_SLOTS + 5) * 8 + 16; }
 
 size_t c3_weight_bytes(int NOUT) { return (size_t)9 * (NOUT / 8) * 3 * NOUT * 16; }
 
@@ -460,7 +363,7 @@ int c3_pack(const float *src, __nv_bfloat16 *dst, int cout, int cin, int NOUT, c
     return JHN_OK;
 }
 
-template <int NOUT, int EW, bool NORM_IN>
+template <int NOUT, int EW>
 static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st)
 {
     static bool configured = false;                                            // per instantiation; attribute is per device, set on first use
@@ -470,23 +373,15 @@ static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st
     if (!configured || configured_dev != dev) {
         int max_smem = 0;
         JHN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        JHN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<NOUT, EW, NORM_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        JHN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<NOUT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true; configured_dev = dev;
     }
-    constexpr int threads = 64 + 128 * EW + (NORM_IN ? C3_XF_THREADS : 0);
-    JHN_LAUNCH(NORM_IN ? "tc_conv3_stacked_norm" : "tc_conv3_stacked", st, tc_conv3_kernel<NOUT, EW, NORM_IN><<<grid, threads, smem, st>>>(L));
+    JHN_LAUNCH("tc_conv3_stacked", st, tc_conv3_kernel<NOUT, EW><<<grid, 64 + 128 * EW, smem, st>>>(L));
     return JHN_OK;
 }
-template <int NOUT, int EW>
-static int c3_launch_n(const C3Launch &L, int grid, size_t smem, cudaStream_t st)
-{
-    return L.in_stats.part ? c3_launch_t<NOUT, EW, true>(L, grid, smem, st) : c3_launch_t<NOUT, EW, false>(L, grid, smem, st);
-}
 
-// `in_stats` non-null: `in` is the raw output of the previous convolution; InstanceNorm (statistics `in_stats`, over `D^3` voxels)
-// + ReLU are applied on load.
 int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, StatPart *stats, int B, int D,
-              int NS, int PB, int sms, int add_bias, const StatPart *in_stats, cudaStream_t st)
+              int NS, int PB, int sms, int add_bias, cudaStream_t st)
 {
     C3Launch L;
     L.in = (const uint4 *)in; L.w = w; L.bias = bias; L.out = (uint4 *)out; L.B = B; L.D = D;
@@ -494,18 +389,16 @@ int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bia
     L.NT = cdiv((long long)(D - 1) * Wp + D, C3_VALID);
     L.total_tiles = B * L.NT * D;
     L.NS = NS; L.PB = PB; L.add_bias = add_bias;
-    L.in_stats = in_stats ? *in_stats : StatPart{nullptr, 0, 0, 0};
-    L.in_inv_count = 1.f / (float)(D * D * D); L.in_eps = 1e-5f;               // as TcCtx::norm
     const size_t smem = c3_weight_bytes(NOUT) + (size_t)NS * (NOUT / 8) * PB * 16 + c3_tail_bytes(NOUT);
     const int grid = L.total_tiles < sms ? L.total_tiles : sms;
     if (stats) { stats->grid = grid; stats->Tb = L.NT * D; stats->T = L.total_tiles; L.stats = *stats; }
     else L.stats = StatPart{nullptr, 0, 0, 0};
     switch (NOUT) {
-    case 16: return c3_launch_n<16, 2>(L, grid, smem, st);
-    case 32: return c3_launch_n<32, 2>(L, grid, smem, st);
-    case 48: return c3_launch_n<48, C3_EW48>(L, grid, smem, st);
-    case 64: return c3_launch_n<64, 2>(L, grid, smem, st);
-    case 80: return c3_launch_n<80, 2>(L, grid, smem, st);
+    case 16: return c3_launch_t<16, 2>(L, grid, smem, st);
+    case 32: return c3_launch_t<32, 2>(L, grid, smem, st);
+    case 48: return c3_launch_t<48, C3_EW48>(L, grid, smem, st);
+    case 64: return c3_launch_t<64, 2>(L, grid, smem, st);
+    case 80: return c3_launch_t<80, 2>(L, grid, smem, st);
     }
     return fail(JHN_ERR_SHAPE, "stacked 3x3x3 kernel: unsupported channel width %d", NOUT);
 }

@@ -460,39 +460,16 @@ int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st
 // per (sample, 8-channel chunk, z-plane) walks the plane's contiguous run of padded positions with 16-byte
 // accesses; the 8 (mean, rstd) pairs are computed once per block, pad columns are skipped (they stay zero).
 constexpr int NORM_THREADS = 256, NORM_UNROLL = 3, NORM_ZB = 4;      // NORM_ZB z-planes per block: the statistics prologue is paid once per 4 planes
-// RES_RAW: `residual` is itself the raw output of a convolution whose InstanceNorm + ReLU were never materialised (they
-// are applied on load by the stacked 3x3x3 kernel, conv3_tc.cu); its normalised, bf16-rounded value is rebuilt here from
-// `res_stats` — the same bits the separate pass would have stored.
-template <bool HAS_RES, bool HAS_POST, bool HAS_PS, bool RES_RAW>
+template <bool HAS_RES, bool HAS_POST, bool HAS_PS>
 __global__ void __launch_bounds__(NORM_THREADS)
-tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__restrict__ residual, const StatPart res_stats,
+tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__restrict__ residual,
                    const uint4 *__restrict__ post_add, uint4 *__restrict__ ps_out, int relu, int D, int CJ, int NOUT,
                    float inv_count, float eps, uint32_t wp_magic)
 {
-    __shared__ float sc[32];                                          // mean[8], rstd[8], residual mean[8], rstd[8]
+    __shared__ float sc[16];                                          // mean[8], rstd[8]
     __shared__ double red[32][8][2];
     const int bj = blockIdx.y, b = bj / CJ, j = bj - b * CJ;
     const int Wp = D + 2, PP = Wp * Wp;
-    if (RES_RAW) {
-        const int c0 = stat_owner((long long)b * res_stats.Tb, res_stats.grid, res_stats.T);
-        const int c1 = stat_owner((long long)(b + 1) * res_stats.Tb - 1, res_stats.grid, res_stats.T);
-        const int nslots = (c1 - c0 + 1) * 4;
-        const int ch = threadIdx.x & 7, grp = threadIdx.x >> 3;
-        const float2 *src = reinterpret_cast<const float2 *>(res_stats.part) + (size_t)(c0 + b) * 4 * NOUT + j * 8 + ch;
-        double s1 = 0.0, s2 = 0.0;
-        for (int s = grp; s < nslots; s += NORM_THREADS / 8) { const float2 v = src[(size_t)s * NOUT]; s1 += (double)v.x; s2 += (double)v.y; }
-        red[grp][ch][0] = s1; red[grp][ch][1] = s2;
-        __syncthreads();
-        if (threadIdx.x < 8) {
-            double t1 = 0.0, t2 = 0.0;
-            for (int g = 0; g < NORM_THREADS / 8; ++g) { t1 += red[g][threadIdx.x][0]; t2 += red[g][threadIdx.x][1]; }
-            const double mean = t1 * (double)inv_count;
-            const double var = fmax(t2 * (double)inv_count - mean * mean, 0.0);
-            sc[16 + threadIdx.x] = (float)mean;
-            sc[24 + threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
-        }
-        __syncthreads();
-    }
     {
         // second stage of the statistics: the producing kernel's per-CTA slots of sample b, added in slot order in fp64
         // (strided over 32 thread groups, then a fixed-order sum over the groups): identical bits on every run
@@ -515,9 +492,9 @@ tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__r
         sc[8 + threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
-    float mean[8], rstd[8], rmean[8], rrstd[8];
+    float mean[8], rstd[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { mean[i] = sc[i]; rstd[i] = sc[8 + i]; rmean[i] = RES_RAW ? sc[16 + i] : 0.f; rrstd[i] = RES_RAW ? sc[24 + i] : 0.f; }
+    for (int i = 0; i < 8; ++i) { mean[i] = sc[i]; rstd[i] = sc[8 + i]; }
     const int p_begin = Wp + 1, p_end = D * Wp + D + 1;               // first / one-past-last interior position
     const int Dh = D / 2, Wh = Dh + 2;
     const int z_end = min(D, ((int)blockIdx.x + 1) * NORM_ZB);
@@ -551,16 +528,7 @@ tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__r
             for (int i = 0; i < 4; ++i) {
                 float f0 = (__uint_as_float(w[i] << 16) - mean[2 * i]) * rstd[2 * i];
                 float f1 = (__uint_as_float(w[i] & 0xffff0000u) - mean[2 * i + 1]) * rstd[2 * i + 1];
-                if (HAS_RES) {
-                    float r0 = __uint_as_float(rw[i] << 16), r1 = __uint_as_float(rw[i] & 0xffff0000u);
-                    if (RES_RAW) {                                     // relu(norm(raw)) rounded to bf16, as the separate pass stores it
-                        r0 = fmaxf((r0 - rmean[2 * i]) * rrstd[2 * i], 0.f);
-                        r1 = fmaxf((r1 - rmean[2 * i + 1]) * rrstd[2 * i + 1], 0.f);
-                        const float2 rr = __bfloat1622float2(__floats2bfloat162_rn(r0, r1));
-                        r0 = rr.x; r1 = rr.y;
-                    }
-                    f0 += r0; f1 += r1;
-                }
+                if (HAS_RES) { f0 += __uint_as_float(rw[i] << 16); f1 += __uint_as_float(rw[i] & 0xffff0000u); }
                 if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
                 if (HAS_POST) { f0 += __uint_as_float(pw[i] << 16); f1 += __uint_as_float(pw[i] & 0xffff0000u); }
                 __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
@@ -656,7 +624,7 @@ size_t c3_weight_bytes(int NOUT);
 bool c3_plan(int NOUT, int D, int max_smem, int *NS, int *PB);
 int c3_pack(const float *src, __nv_bfloat16 *dst, int cout, int cin, int NOUT, cudaStream_t st);
 int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bias, void *out, StatPart *stats, int B, int D,
-              int NS, int PB, int sms, int add_bias, const StatPart *in_stats, cudaStream_t st);
+              int NS, int PB, int sms, int add_bias, cudaStream_t st);
 
 struct TcLayer {
     TcProgram prog;
@@ -672,7 +640,6 @@ struct TcNet {
     void *blob;
     int max_smem;
     bool legacy_k3;                                   // JHN_CONV3_LEGACY=1: tap-per-MMA kernel for A/B measurements
-    bool fuse_norm;                                   // InstanceNorm + ReLU applied on load by the stacked kernel (JHN_NORM_FUSE=1; default: separate passes)
 };
 
 static bool c3_eligible(const LayerDesc &d, int kind, int cin_pad, int cout_pad)
@@ -779,8 +746,6 @@ int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st)
     tc->blob = nullptr; tc->max_smem = max_smem;
     const char *leg = getenv("JHN_CONV3_LEGACY");
     tc->legacy_k3 = leg && leg[0] == '1';
-    const char *nf = getenv("JHN_NORM_FUSE");
-    tc->fuse_norm = nf && nf[0] == '1';                // opt-in: measured slower on the B200 (run r2_run7: 3.41 vs 3.28 ms per step), see DESIGN.md
     net->tc = tc;
     size_t total = 0;
     for (int l = 0; l < NUM_LAYERS; ++l) {
@@ -865,23 +830,13 @@ struct TcCtx {
     bool keep_bias;                                   // debug hook: raw conv output incl. bias; forward: an InstanceNorm follows
 
     // in: BP or PS tensor with `chunks_in` chunks per sample on grid side D (the GEMM-row grid)
-    // can layer l on grid side D take a raw input and normalise it on load?  (stacked kernel with a ring deep enough for
-    // three planes in use, one being normalised and one in flight)
-    bool norm_on_load(int l, int D) const
-    {
-        const TcLayer &T = net->tc->layer[l];
-        int ns = 0, pb = 0;
-        return net->tc->fuse_norm && T.w3 && !net->tc->legacy_k3 && c3_plan(T.cout_pad, D, net->tc->max_smem, &ns, &pb) && ns >= 5;
-    }
-    // `in_stats` non-null (only with norm_on_load(l, D)): `in` is raw, InstanceNorm + ReLU applied on load
-    int conv(int l, const uint4 *in, int chunks_in, int D, void *out, int chunks_out, StatPart *stats, const StatPart *in_stats = nullptr) const
+    int conv(int l, const uint4 *in, int chunks_in, int D, void *out, int chunks_out, StatPart *stats) const
     {
         const TcLayer &T = net->tc->layer[l];
         int ns = 0, pb = 0;
         if (T.w3 && !net->tc->legacy_k3 && chunks_in == T.cin_pad / 8 && chunks_out == T.cout_pad / 8 &&
             c3_plan(T.cout_pad, D, net->tc->max_smem, &ns, &pb))
-            return c3_launch(T.cout_pad, in, T.w3, T.bias, out, stats, B, D, ns, pb, sms, keep_bias ? 1 : 0, in_stats, st);
-        if (in_stats) return fail(JHN_ERR_ARG, "normalise-on-load needs the stacked 3x3x3 kernel (layer %d, grid side %d)", l, D);
+            return c3_launch(T.cout_pad, in, T.w3, T.bias, out, stats, B, D, ns, pb, sms, keep_bias ? 1 : 0, st);
         TcProgram P;
         JHN_TRY(build_program(P, kLayerKind[l], T.cin_pad, T.cout_pad, D, net->tc->max_smem));
         P.KC_load = (net->desc[l].cin + 7) / 8 < P.KC ? (net->desc[l].cin + 7) / 8 : P.KC;
@@ -897,25 +852,21 @@ struct TcCtx {
         JHN_LAUNCH(name, st, tc_conv_kernel<<<grid, TC_THREADS, program_smem(P), st>>>(P, L));
         return JHN_OK;
     }
-    // `res_stats` non-null: `residual` is a raw convolution output whose InstanceNorm + ReLU are rebuilt on the fly
-    int norm(uint4 *x, const StatPart &stats, int l, int D, const uint4 *residual, bool relu, const uint4 *post_add, uint4 *ps,
-             const StatPart *res_stats = nullptr) const
+    int norm(uint4 *x, const StatPart &stats, int l, int D, const uint4 *residual, bool relu, const uint4 *post_add, uint4 *ps) const
     {
-        const StatPart rst = res_stats ? *res_stats : StatPart{nullptr, 0, 0, 0};
         const TcLayer &T = net->tc->layer[l];
         const int nv = D * D * D, CJ = T.cout_pad / 8, Wp = D + 2;
         const uint32_t magic = (uint32_t)((0x100000000ull + (unsigned)Wp - 1) / (unsigned)Wp);   // ceil(2^32 / Wp)
         const dim3 grid(cdiv(D, NORM_ZB), B * CJ);
         const float inv = 1.f / (float)nv;
-#define JHN_NORM(R, P, S, W)                                                                                           \
+#define JHN_NORM(R, P, S)                                                                                              \
         JHN_LAUNCH("tc_norm_act_kernel", st,                                                                           \
-                   (tc_norm_act_kernel<R, P, S, W><<<grid, NORM_THREADS, 0, st>>>(x, stats, residual, rst, post_add, ps, relu ? 1 : 0, D, \
-                                                                                  CJ, T.cout_pad, inv, 1e-5f, magic)))
-        if (res_stats && !residual) return fail(JHN_ERR_ARG, "norm: residual statistics without a residual");
-        if (residual && post_add && !ps) { if (res_stats) JHN_NORM(true, true, false, true); else JHN_NORM(true, true, false, false); }
-        else if (residual && !post_add && ps) { if (res_stats) JHN_NORM(true, false, true, true); else JHN_NORM(true, false, true, false); }
-        else if (residual && !post_add && !ps && !res_stats) JHN_NORM(true, false, false, false);
-        else if (!residual && !post_add && !ps) JHN_NORM(false, false, false, false);
+                   (tc_norm_act_kernel<R, P, S><<<grid, NORM_THREADS, 0, st>>>(x, stats, residual, post_add, ps, relu ? 1 : 0, D, CJ, \
+                                                                               T.cout_pad, inv, 1e-5f, magic)))
+        if (residual && post_add && !ps) JHN_NORM(true, true, false);
+        else if (residual && !post_add && ps) JHN_NORM(true, false, true);
+        else if (residual && !post_add && !ps) JHN_NORM(true, false, false);
+        else if (!residual && !post_add && !ps) JHN_NORM(false, false, false);
         else return fail(JHN_ERR_ARG, "norm: unsupported operand combination");
 #undef JHN_NORM
         return JHN_OK;
@@ -977,20 +928,15 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
     for (int i = 0; i < 11; ++i) sp[i] = StatPart{t.stats + (size_t)i * stat_slots(256, carveB) * 96 * 2, 0, 0, 0};
     auto S = [&](int i) { return &sp[i]; };
 
-    // Res3DBlocks on the h grid: when the stacked kernel can normalise on load (fz), the InstanceNorm + ReLU in front of a
-    // 3x3x3 convolution is never a pass of its own — the tensor stays raw and its consumers (the convolution's transform
-    // warps; the block-closing pass that adds it as the residual) rebuild the normalised value from the statistics.
-    const bool fz = c.norm_on_load(L_FRONT1A, h) && c.norm_on_load(L_FRONT1B, h) && c.norm_on_load(L_SKIPB, h) &&
-                    c.norm_on_load(L_DECA, h) && c.norm_on_load(L_DECB, h);
     JHN_TRY(c.conv(L_FRONT0, vol, 8 * j1, h, t.A, j2, S(0)));                         // front_layers.0   v2vnet.py:90
-    if (!fz) JHN_TRY(c.norm(t.A, *S(0), L_FRONT0, h, nullptr, true, nullptr, nullptr));
-    JHN_TRY(c.conv(L_FRONT1A, t.A, j2, h, t.Bq, j2, S(1), fz ? S(0) : nullptr));      // front_layers.1 (Res3DBlock)
-    if (!fz) JHN_TRY(c.norm(t.Bq, *S(1), L_FRONT1A, h, nullptr, true, nullptr, nullptr));
-    JHN_TRY(c.conv(L_FRONT1B, t.Bq, j2, h, t.C, j2, S(2), fz ? S(1) : nullptr));
-    JHN_TRY(c.norm(t.C, *S(2), L_FRONT1B, h, t.A, true, nullptr, t.Xps, fz ? S(0) : nullptr));   // x = C (+ PS copy for the pool)
+    JHN_TRY(c.norm(t.A, *S(0), L_FRONT0, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_FRONT1A, t.A, j2, h, t.Bq, j2, S(1)));                           // front_layers.1 (Res3DBlock)
+    JHN_TRY(c.norm(t.Bq, *S(1), L_FRONT1A, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_FRONT1B, t.Bq, j2, h, t.C, j2, S(2)));
+    JHN_TRY(c.norm(t.C, *S(2), L_FRONT1B, h, t.A, true, nullptr, t.Xps));              // x = C (+ PS copy for the pool)
     JHN_TRY(c.conv(L_SKIPA, t.C, j2, h, t.A, j2, S(3)));                              // skip_res1        :76
-    if (!fz) JHN_TRY(c.norm(t.A, *S(3), L_SKIPA, h, nullptr, true, nullptr, nullptr));
-    JHN_TRY(c.conv(L_SKIPB, t.A, j2, h, t.Bq, j2, S(4), fz ? S(3) : nullptr));
+    JHN_TRY(c.norm(t.A, *S(3), L_SKIPA, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_SKIPB, t.A, j2, h, t.Bq, j2, S(4)));
     JHN_TRY(c.norm(t.Bq, *S(4), L_SKIPB, h, t.C, true, nullptr, nullptr));             // s = Bq
     JHN_TRY(c.conv(L_POOL, t.Xps, 8 * j2, q, t.Pq, j4, S(5)));                        // encoder_pool1    :77
     JHN_TRY(c.norm(t.Pq, *S(5), L_POOL, q, nullptr, true, nullptr, nullptr));
@@ -999,11 +945,11 @@ int tc_forward(const jhn_v2v *net, const void *volume_in, int in_layout, int B, 
     JHN_TRY(c.conv(L_MIDB, t.Q, j4, q, t.R, j4, S(7)));
     JHN_TRY(c.norm(t.R, *S(7), L_MIDB, q, t.Pq, true, nullptr, nullptr));
     JHN_TRY(c.conv(L_UP, t.R, j4, q, t.A, j2, S(8)));                                 // decoder_upsample1 :79
-    if (!fz) JHN_TRY(c.norm(t.A, *S(8), L_UP, h, nullptr, true, nullptr, nullptr));
-    JHN_TRY(c.conv(L_DECA, t.A, j2, h, t.Dd, j2, S(9), fz ? S(8) : nullptr));         // decoder_res1     :80
-    if (!fz) JHN_TRY(c.norm(t.Dd, *S(9), L_DECA, h, nullptr, true, nullptr, nullptr));
-    JHN_TRY(c.conv(L_DECB, t.Dd, j2, h, t.E, j2, S(10), fz ? S(9) : nullptr));
-    JHN_TRY(c.norm(t.E, *S(10), L_DECB, h, t.A, true, t.Bq, nullptr, fz ? S(8) : nullptr));   // relu(.. + x) + skip   :81
+    JHN_TRY(c.norm(t.A, *S(8), L_UP, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_DECA, t.A, j2, h, t.Dd, j2, S(9)));                              // decoder_res1     :80
+    JHN_TRY(c.norm(t.Dd, *S(9), L_DECA, h, nullptr, true, nullptr, nullptr));
+    JHN_TRY(c.conv(L_DECB, t.Dd, j2, h, t.E, j2, S(10)));
+    JHN_TRY(c.norm(t.E, *S(10), L_DECB, h, t.A, true, t.Bq, nullptr));                 // relu(.. + x) + skip   :81
     if (tail) {                                                                        // output_layer + model.py:73-87
         const TcLayer &H = tc->layer[L_HEAD];
         return head_centroid_launch(t.E, H.w, H.bias, B, h, net->K, H.cin_pad, H.cout_pad, tail->spacing, tail->roi, tail->center3D,

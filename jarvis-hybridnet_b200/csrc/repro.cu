@@ -415,7 +415,10 @@ constexpr int G_PIX_BYTES = KP * 2;                                           //
 // Packed fp32x2 arithmetic (sm_100 FMUL2 / FFMA2 / FADD2): the x and the y pixel coordinate of a corner travel
 // as one 64-bit register pair through the three nested lerps, each half an IEEE round-to-nearest fp32
 // operation exactly like the scalar instruction — half the issue slots of the index chain.
-// f2_pack: tc_ptx.cuh
+__device__ __forceinline__ uint64_t f2_pack(float x, float y)
+{
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r;
+}
 __device__ __forceinline__ void f2_unpack(uint64_t v, float &x, float &y)
 {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));

@@ -100,27 +100,5 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int N)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
-// ------------------------------------------------------------------------------------------------
-// InstanceNorm + ReLU arithmetic shared by tc_norm_act_kernel (conv_tc.cu) and the normalise-on-load transform of the stacked
-// 3x3x3 kernel (conv3_tc.cu): y = fma(x, scale, shift) with scale = rstd, shift = -mean * rstd (one rounding each), ReLU and
-// the bf16 rounding in one cvt.  Both paths call these, so they agree bit for bit.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 norm_scale_shift(float mean, float rstd) { return make_float2(rstd, __fmul_rn(-mean, rstd)); }
-__device__ __forceinline__ uint64_t f2_pack(float x, float y)
-{
-    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r;
-}
-// w = two bf16 (channel c in the low half, c + 1 in the high half); sc / sh = (scale_c, scale_c+1) / (shift_c, shift_c+1)
-__device__ __forceinline__ uint32_t norm_relu_bf16x2(uint32_t w, uint64_t sc, uint64_t sh)
-{
-    const uint64_t x = f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
-    uint64_t y;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y) : "l"(x), "l"(sc), "l"(sh));
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(y));
-    uint32_t r;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
 
 }  // namespace jhn

@@ -274,25 +274,3 @@ def test_sub_batch_invariance():
         assert torch.equal(torch.cat(one), outs[1][0])              # pass size 1 == seven B=1 calls, bit for bit
     finally:
         _lib.set_sub_batch(0)
-
-
-@pytest.mark.parametrize("K,G,B", [(23, 72, 2), (23, 24, 3), (5, 40, 1), (23, 64, 1)])
-def test_norm_on_load_equals_separate_passes(K, G, B):
-    """The stacked 3x3x3 kernel applies InstanceNorm + ReLU to its raw input on load (conv3_tc.cu, transform warps) and the
-    block-closing pass rebuilds the raw residual (opt-in, JHN_NORM_FUSE=1): same arithmetic as the separate tc_norm_act passes,
-    so the whole V2V output must agree bit for bit (v2vnet.py:18-19,33-34,41-43,54-55)."""
-    import jarvis_hybridnet_b200.synth as S
-    w = S.make_v2v_weights(K, 5, "he")
-    g = torch.Generator(device="cpu").manual_seed(7)
-    x = torch.rand((B, K, G, G, G), generator=g).to(DEV)
-    outs = []
-    for fuse in ("1", "0"):
-        os.environ["JHN_NORM_FUSE"] = fuse
-        try:
-            net = make_net(K, w)
-            outs.append(net(x).clone())
-        finally:
-            os.environ.pop("JHN_NORM_FUSE", None)
-        del net
-    assert torch.isfinite(outs[0]).all()
-    assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max().item()
