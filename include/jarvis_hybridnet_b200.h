@@ -223,7 +223,8 @@ int jhn_crop_normalize(const float *imgs, int B, int ncam, int H, int W, int bbo
  * jhn_ingest_frames: jarvis/prediction/predict3D.py:79
  *     `torch.from_numpy(imgs_orig).cuda().float().permute(0,3,1,2)[:, [2,1,0]] / 255.`
  *   frames  device uint8 [N][H][W][3], BGR as cv2.VideoCapture.read() delivers them (N = cameras x frame sets)
- *   imgs    device fp32  [N][3][H][W], RGB, float(u8) / 255 (one rounded division: the reference's bits).  W % 4 == 0.
+ *   imgs    device fp32  [N][3][H][W], RGB, float(u8) * (1.f / 255.f): the bits of the reference's CUDA tensor (ATen divides by a
+ *           Python scalar as a multiplication by its fp32 reciprocal).  W % 4 == 0.
  * jhn_crop_normalize_u8: jarvis/prediction/jarvis3D.py:168-177 straight from the uint8 frames:
  *   crops device fp32 [B][ncam][3][bbox][bbox] = ((u8 / 255) - mean) / std around centerHM; zeros where valid == 0.
  *   Same values as jhn_ingest_frames followed by jhn_crop_normalize, without the fp32 image.

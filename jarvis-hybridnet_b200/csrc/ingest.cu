@@ -3,9 +3,12 @@
 //   ingest_frames_kernel      jarvis/prediction/predict3D.py:79  `from_numpy(imgs_orig).cuda().float().permute(0,3,1,2)[:, [2,1,0]] / 255.`
 //                             decoded frames cross PCIe as the decoder wrote them (uint8, H x W x BGR: 3 B per pixel instead of
 //                             the 12 B of the fp32 tensor the reference uploads) and become the reference's fp32 CHW RGB tensor
-//                             on the device: float(u8) / 255 as ONE rounded fp32 division, the same bits torch produces.
+//                             on the device.  ATen's CUDA division by a Python scalar multiplies by the fp32 reciprocal
+//                             (BinaryDivTrueKernel.cu: `a * (1 / b)`), so the reference's tensor is float(u8) * (1.f / 255.f);
+//                             the kernel produces those bits (they differ from the IEEE quotient in the last place for
+//                             some byte values).
 //   crop_normalize_u8_kernel  jarvis/prediction/jarvis3D.py:168-177 straight from the uint8 frames: the key-point detector's
-//                             crops ((u8 / 255 - mean) / std, three separately rounded fp32 ops as in the reference) without
+//                             crops ((u8 * (1/255) - mean) / std, three separately rounded fp32 ops as the reference's CUDA path) without
 //                             ever materialising the 12 x 3 x 1024 x 1280 fp32 image in HBM.
 //   softplus2_kernel          jarvis/hybridnet/model.py:73,88   heatmap_final = softplus(softplus(v2v))  (the returned volume)
 //   pad_border_kernel         jarvis/hybridnet/model.py:65-66   heatmaps_padded = F.pad(heatmaps, [1,1,1,1])
@@ -32,10 +35,10 @@ ingest_frames_kernel(const uint8_t *__restrict__ frames, int H, int W, long long
     const float r2 = (float)(w2 & 0xffu), b3 = (float)((w2 >> 8) & 0xffu), g3 = (float)((w2 >> 16) & 0xffu), r3 = (float)(w2 >> 24);
     const size_t plane = (size_t)H * W;
     float *dst = out + (size_t)img * 3 * plane + (size_t)y * W + x4;
-    const float d = 255.f;
-    *reinterpret_cast<float4 *>(dst) = make_float4(__fdiv_rn(r0, d), __fdiv_rn(r1, d), __fdiv_rn(r2, d), __fdiv_rn(r3, d));
-    *reinterpret_cast<float4 *>(dst + plane) = make_float4(__fdiv_rn(g0, d), __fdiv_rn(g1, d), __fdiv_rn(g2, d), __fdiv_rn(g3, d));
-    *reinterpret_cast<float4 *>(dst + 2 * plane) = make_float4(__fdiv_rn(b0, d), __fdiv_rn(b1, d), __fdiv_rn(b2, d), __fdiv_rn(b3, d));
+    const float d = __fdiv_rn(1.f, 255.f);                           // ATen CUDA `x / 255.` == x * (1.f / 255.f)
+    *reinterpret_cast<float4 *>(dst) = make_float4(__fmul_rn(r0, d), __fmul_rn(r1, d), __fmul_rn(r2, d), __fmul_rn(r3, d));
+    *reinterpret_cast<float4 *>(dst + plane) = make_float4(__fmul_rn(g0, d), __fmul_rn(g1, d), __fmul_rn(g2, d), __fmul_rn(g3, d));
+    *reinterpret_cast<float4 *>(dst + 2 * plane) = make_float4(__fmul_rn(b0, d), __fmul_rn(b1, d), __fmul_rn(b2, d), __fmul_rn(b3, d));
 }
 
 // out[b][c][ch][y][x] = ((frames[b][c][cy - hw + y][cx - hw + x][2 - ch] / 255) - mean[ch]) / std[ch]; zeros when !valid[b].
@@ -59,7 +62,8 @@ crop_normalize_u8_kernel(const uint8_t *__restrict__ frames, int H, int W, int b
         const uint8_t *src = frames + (((size_t)bc * H + (cy - hw + y)) * W + (cx - hw + x4)) * 3;
         float v[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = __fdiv_rn((float)__ldg(src + i), 255.f);     // pixel i / 3, BGR channel i % 3
+        const float d = __fdiv_rn(1.f, 255.f);
+        for (int i = 0; i < 12; ++i) v[i] = __fmul_rn((float)__ldg(src + i), d);          // pixel i / 3, BGR channel i % 3
         const float m[3] = {m0, m1, m2}, s[3] = {s0, s1, s2};
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {                              // output plane ch = RGB, input byte 2 - ch

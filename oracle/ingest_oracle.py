@@ -16,9 +16,13 @@ import numpy as np
 f32 = np.float32
 
 
-def ingest_frames(frames):
-    """uint8 [N,H,W,3] BGR -> fp32 [N,3,H,W] RGB, float(u8) / 255 (one rounded division)."""
+def ingest_frames(frames, cuda_scalar_division=True):
+    """uint8 [N,H,W,3] BGR -> fp32 [N,3,H,W] RGB in [0,1].  predict3D.py:79 runs on the GPU, where ATen divides by a Python
+    scalar as `x * (1.f / 255.f)` (aten/src/ATen/native/cuda/BinaryDivTrueKernel.cu); cuda_scalar_division=False gives the
+    IEEE quotient ATen's CPU kernel returns (the two differ in the last place for some byte values)."""
     x = frames.astype(f32).transpose(0, 3, 1, 2)[:, [2, 1, 0]]
+    if cuda_scalar_division:
+        return (x * (f32(1.) / f32(255.))).astype(f32)
     return (x / f32(255.)).astype(f32)
 
 

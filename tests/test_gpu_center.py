@@ -82,7 +82,7 @@ def test_accelerate_predictor_seam():
     p.bbox_hw, p.bounding_box_size, p.num_cameras, p.center_detect_img_size = x["bbox"] // 2, x["bbox"], 12, x["cdis"]
     import jarvis_hybridnet_b200.model as M
     orig = M.accelerate
-    M.accelerate = lambda bb, precision="fp32": bb            # the 3D seam has its own test (test_accelerate_seam)
+    M.accelerate = lambda bb, precision="fp32", **kw: bb            # the 3D seam has its own test (test_accelerate_seam)
     try:
         accelerate_predictor(p)
     finally:

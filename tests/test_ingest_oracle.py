@@ -19,9 +19,13 @@ def frames_u8(B, ncam, H, W, seed=0):
 def test_ingest_matches_predict3D_line_79():
     fr = frames_u8(1, 3, 20, 24)[0]
     want = (torch.from_numpy(fr).float().permute(0, 3, 1, 2)[:, [2, 1, 0]] / 255.).numpy()
-    assert np.array_equal(IO.ingest_frames(fr), want)
+    assert np.array_equal(IO.ingest_frames(fr, cuda_scalar_division=False), want)       # ATen CPU: IEEE quotient
+    # ATen CUDA (the reference's path, `.cuda()` is hard-wired): multiplication by the fp32 reciprocal; tests/test_gpu_ingest.py
+    # holds the oracle's default to torch's CUDA result on the B200
+    assert np.array_equal(IO.ingest_frames(fr), (torch.from_numpy(fr).float().permute(0, 3, 1, 2)[:, [2, 1, 0]] * (torch.tensor(1.) / 255.)).numpy())
+    assert np.abs(IO.ingest_frames(fr) - want).max() <= 2 ** -24
     allv = np.arange(256, dtype=np.uint8).reshape(1, 1, 256, 1).repeat(3, 3)        # every byte value: [1,1,256,3]
-    assert np.array_equal(IO.ingest_frames(allv)[0, 0, 0, :], (torch.arange(256).float() / 255.).numpy())
+    assert np.array_equal(IO.ingest_frames(allv, cuda_scalar_division=False)[0, 0, 0, :], (torch.arange(256).float() / 255.).numpy())
 
 
 def test_crop_matches_jarvis3D_lines_168_177():
@@ -31,7 +35,7 @@ def test_crop_matches_jarvis3D_lines_168_177():
     chm = np.stack([rng.integers(8, W - 8, (B, ncam)), rng.integers(8, H - 8, (B, ncam))], -1).astype(np.int32)
     mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
     got = IO.crop_normalize_u8(fr, chm, np.array([1, 0]), bbox, mean, std)
-    imgs = torch.from_numpy(fr[0]).float().permute(0, 3, 1, 2)[:, [2, 1, 0]] / 255.
+    imgs = torch.from_numpy(fr[0]).float().permute(0, 3, 1, 2)[:, [2, 1, 0]] * (torch.tensor(1.) / 255.)    # CUDA semantics of `/ 255.`
     tm, ts = torch.tensor(mean).view(3, 1, 1), torch.tensor(std).view(3, 1, 1)
     hw = bbox // 2
     want = torch.zeros(ncam, 3, bbox, bbox)
