@@ -126,6 +126,30 @@ int jhn_reproject_gather(const void *heatmaps, int hm_format, int heatmaps_padde
 int jhn_heatmap_convert(const float *heatmaps, int heatmaps_padded, int B, int ncam, int K, int hs,
                         int dst_format, void *dst, jhn_stream_t stream);
 
+/* Host-buffer callers (the end-to-end path of HybridNet3D.forward_host): the gather of one frame set reads, per camera,
+ * only the pixels inside the projection of the voxel grid — 57 % of a 130x130 map at the Example shape, 12 % of a 258x258
+ * map at the micro-benchmark shape.
+ *   jhn_heatmap_boxes         runs the projection of repro_layer.py:46-68 for the coarse grid and returns, per (frame set,
+ *                             camera), the pixel box {x0, y0, -x1, -y1} (padded heat-map pixels, inclusive) that bounds every
+ *                             index jhn_reproject_gather / jhn_hybrid3d_forward will read for these centres and calibration.
+ *                             boxes: device i32 [B][ncam][4].
+ *   jhn_upload_heatmap_boxes  host code: one cudaMemcpy2DAsync per image that copies just that box of a channels-last host
+ *                             tensor [n_images][hs][hs][pixel_bytes] (pinned) to the same place of the device tensor; the
+ *                             pixels outside the boxes are never read by the gather and may hold anything.
+ *                             boxes_host: HOST copy of jhn_heatmap_boxes' output; bytes_copied (optional) = bytes moved. */
+int jhn_heatmap_boxes(const float *cameraMatrices, const float *intrinsicMatrices, const float *distortionCoefficients,
+                      const float *center3D, const int32_t *centerHM, int B, int ncam, int hs, int G, float spacing,
+                      int32_t *boxes, jhn_stream_t stream);
+int jhn_upload_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, const int32_t *boxes_host, int n_images, int hs,
+                             int pixel_bytes, jhn_stream_t stream, size_t *bytes_copied);
+/*   jhn_pull_heatmap_boxes    the same transfer executed by a kernel that reads the boxes straight out of pinned,
+ *                             device-mapped host memory (cudaHostAlloc / torch pin_memory()): no copy-engine row overhead
+ *                             (a strided DMA of 5 KB rows runs at 36 GB/s on a B200, a contiguous one at 55 GB/s), and `boxes`
+ *                             is the DEVICE tensor jhn_heatmap_boxes wrote, so nothing synchronises with the host.
+ *                             bytes_pulled (optional, device u64) is incremented by the bytes read over the link. */
+int jhn_pull_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, const int32_t *boxes, int n_images, int hs,
+                           int pixel_bytes, unsigned long long *bytes_pulled, jhn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 2 — replaces V2VNet (jarvis/hybridnet/v2vnet.py:86-102) in eval mode.
  *

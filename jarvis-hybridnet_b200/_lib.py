@@ -41,6 +41,9 @@ SYMBOLS = {
     "jhn_center_locate": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P,
                                   _P, _P, _P, _P, _P, _P, _P, _P]),
     "jhn_crop_normalize": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, POINTER(c_float), POINTER(c_float), _P, _P]),
+    "jhn_heatmap_boxes": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P]),
+    "jhn_upload_heatmap_boxes": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, POINTER(c_size_t)]),
+    "jhn_pull_heatmap_boxes": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "jhn_ingest_frames": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "jhn_crop_normalize_u8": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, POINTER(c_float), POINTER(c_float), _P, _P]),
     "jhn_efftrack_head": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),

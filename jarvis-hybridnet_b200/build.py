@@ -16,7 +16,7 @@ SOURCES = ["api.cu", "repro.cu", "conv_f32.cu", "conv_tc.cu", "conv3_tc.cu", "he
            "ingest.cu", "head2d.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-ABI_VERSION = 5                                                        # == jhn_abi_version() of the sources in csrc/
+ABI_VERSION = 6                                                        # == jhn_abi_version() of the sources in csrc/
 
 
 def _headers():

@@ -1,5 +1,6 @@
 // extern "C" surface declared in include/jarvis_hybridnet_b200.h: argument validation, workspace
 // carving and stage sequencing.  No computation lives here.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -83,7 +84,7 @@ using namespace jhn;
 extern "C" {
 
 const char *jhn_last_error(void) { return g_err; }
-int jhn_abi_version(void) { return 5; }
+int jhn_abi_version(void) { return 6; }
 unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
@@ -386,6 +387,122 @@ int jhn_crop_normalize(const float *imgs, int B, int ncam, int H, int W, int bbo
     for (int i = 0; i < 3; ++i)
         if (!(std[i] > 0.f)) return fail(JHN_ERR_ARG, "std[%d] must be > 0", i);
     return crop_normalize_launch(imgs, B, ncam, H, W, bbox, centerHM, valid, mean, std, crops, (cudaStream_t)stream);
+}
+
+int jhn_heatmap_boxes(const float *cameraMatrices, const float *intrinsicMatrices, const float *distortionCoefficients,
+                      const float *center3D, const int32_t *centerHM, int B, int ncam, int hs, int G, float spacing,
+                      int32_t *boxes, jhn_stream_t stream)
+{
+    if (!cameraMatrices || !intrinsicMatrices || !distortionCoefficients || !center3D || !centerHM || !boxes)
+        return fail(JHN_ERR_ARG, "jhn_heatmap_boxes: null pointer argument");
+    if (B < 1 || B > 65535 || ncam < 1 || ncam > 64) return fail(JHN_ERR_SHAPE, "need 1<=B<=65535, 1<=ncam<=64 (got B=%d ncam=%d)", B, ncam);
+    if (hs < 4 || G < 2 || (G & 1)) return fail(JHN_ERR_SHAPE, "need hs>=4 and an even grid side (got hs=%d G=%d)", hs, G);
+    return heatmap_boxes_launch(cameraMatrices, intrinsicMatrices, distortionCoefficients, center3D, centerHM, B, ncam, hs, G, spacing,
+                                boxes, (cudaStream_t)stream);
+}
+
+int jhn_upload_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, const int32_t *boxes_host, int n_images, int hs,
+                             int pixel_bytes, jhn_stream_t stream, size_t *bytes_copied)
+{
+    if (!host_heatmaps || !device_heatmaps || !boxes_host) return fail(JHN_ERR_ARG, "jhn_upload_heatmap_boxes: null pointer argument");
+    if (n_images < 1 || hs < 1 || pixel_bytes < 1) return fail(JHN_ERR_SHAPE, "need n_images>=1, hs>=1, pixel_bytes>=1");
+    const size_t pitch = (size_t)hs * pixel_bytes, img = pitch * hs;
+    size_t total = 0;
+    // mode 0 (default): ONE cudaMemcpy3DBatchAsync for all boxes (a cudaMemcpy2DAsync per image costs the calling thread
+    // ~10 us each — 384 images per 32 frame sets made the host the bottleneck); 1: one 2-D copy per image; 2: one contiguous
+    // copy of the box's rows per image (more bytes, cheapest descriptors)
+    static const int mode = [] { const char *e = getenv("JHN_UPLOAD_MODE"); return e ? atoi(e) : 0; }();
+    std::vector<cudaMemcpy3DBatchOp> ops;
+    if (mode == 0) ops.reserve(n_images);
+    for (int i = 0; i < n_images; ++i) {
+        const int x0 = boxes_host[4 * i + 0], y0 = boxes_host[4 * i + 1], x1 = -boxes_host[4 * i + 2], y1 = -boxes_host[4 * i + 3];
+        if (x0 < 0 || y0 < 0 || x1 >= hs || y1 >= hs || x1 < x0 || y1 < y0)
+            return fail(JHN_ERR_ARG, "image %d: box [%d,%d]x[%d,%d] is not inside the %dx%d map (boxes not computed yet?)", i, x0, x1, y0, y1, hs, hs);
+        const size_t off = (size_t)i * img + (size_t)y0 * pitch + (size_t)x0 * pixel_bytes;
+        const size_t w = (size_t)(x1 - x0 + 1) * pixel_bytes, hgt = (size_t)(y1 - y0 + 1);
+        if (mode == 2) {
+            const size_t roff = (size_t)i * img + (size_t)y0 * pitch;
+            JHN_CUDA(cudaMemcpyAsync((char *)device_heatmaps + roff, (const char *)host_heatmaps + roff, pitch * hgt, cudaMemcpyHostToDevice,
+                                     (cudaStream_t)stream));
+            total += pitch * hgt;
+            continue;
+        }
+        if (mode == 1) {
+            JHN_CUDA(cudaMemcpy2DAsync((char *)device_heatmaps + off, pitch, (const char *)host_heatmaps + off, pitch, w, hgt,
+                                       cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        } else {
+            cudaMemcpy3DBatchOp op{};
+            op.src.type = cudaMemcpyOperandTypePointer;
+            op.src.op.ptr.ptr = (void *)((const char *)host_heatmaps + off);
+            op.src.op.ptr.rowLength = pitch; op.src.op.ptr.layerHeight = 0;
+            op.dst.type = cudaMemcpyOperandTypePointer;
+            op.dst.op.ptr.ptr = (char *)device_heatmaps + off;
+            op.dst.op.ptr.rowLength = pitch; op.dst.op.ptr.layerHeight = 0;
+            op.extent = make_cudaExtent(w, hgt, 1);
+            op.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+            op.flags = 0;
+            ops.push_back(op);
+        }
+        total += w * hgt;
+    }
+    if (mode == 0) {
+        if (!stream) return fail(JHN_ERR_ARG, "jhn_upload_heatmap_boxes needs a non-default stream (cudaMemcpy3DBatchAsync)");
+        // A copy engine spends ~0.16 us per row of a strided copy, i.e. ~35 GB/s on 5 KB rows — below the PCIe link.  The
+        // boxes are therefore split over UP_LANES internal streams (fork / join on the caller's stream with events) so that
+        // several copy engines walk rows concurrently.
+        static const int lanes_env = [] { const char *e = getenv("JHN_UPLOAD_LANES"); return e ? atoi(e) : 0; }();
+        constexpr int UP_LANES_MAX = 8;
+        const int lanes = lanes_env > 0 ? (lanes_env > UP_LANES_MAX ? UP_LANES_MAX : lanes_env) : 4;
+        struct Lanes { cudaStream_t s[UP_LANES_MAX]; cudaEvent_t fork, join[UP_LANES_MAX]; int dev; };
+        static thread_local std::map<int, Lanes> cache;                 // per (thread, device)
+        int dev = 0;
+        JHN_CUDA(cudaGetDevice(&dev));
+        auto it = cache.find(dev);
+        if (it == cache.end()) {
+            Lanes L{};
+            L.dev = dev;
+            for (int i = 0; i < UP_LANES_MAX; ++i) {
+                JHN_CUDA(cudaStreamCreateWithFlags(&L.s[i], cudaStreamNonBlocking));
+                JHN_CUDA(cudaEventCreateWithFlags(&L.join[i], cudaEventDisableTiming));
+            }
+            JHN_CUDA(cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming));
+            it = cache.emplace(dev, L).first;
+        }
+        Lanes &L = it->second;
+        if (lanes <= 1 || ops.size() < 2 * (size_t)lanes) {
+            size_t fail_idx = 0;
+            JHN_CUDA(cudaMemcpy3DBatchAsync(ops.size(), ops.data(), &fail_idx, 0, (cudaStream_t)stream));
+        } else {
+            JHN_CUDA(cudaEventRecord(L.fork, (cudaStream_t)stream));
+            const size_t per = (ops.size() + lanes - 1) / lanes;
+            for (int l = 0; l < lanes; ++l) {
+                const size_t lo = l * per, hi = std::min(ops.size(), lo + per);
+                if (lo >= hi) break;
+                JHN_CUDA(cudaStreamWaitEvent(L.s[l], L.fork, 0));
+                size_t fail_idx = 0;
+                JHN_CUDA(cudaMemcpy3DBatchAsync(hi - lo, ops.data() + lo, &fail_idx, 0, L.s[l]));
+                JHN_CUDA(cudaEventRecord(L.join[l], L.s[l]));
+                JHN_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, L.join[l], 0));
+            }
+        }
+    }
+    if (bytes_copied) *bytes_copied = total;
+    return JHN_OK;
+}
+
+int jhn_pull_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, const int32_t *boxes, int n_images, int hs,
+                           int pixel_bytes, unsigned long long *bytes_pulled, jhn_stream_t stream)
+{
+    if (!host_heatmaps || !device_heatmaps || !boxes) return fail(JHN_ERR_ARG, "jhn_pull_heatmap_boxes: null pointer argument");
+    if (n_images < 1 || n_images > 65535 || hs < 1 || pixel_bytes < 16 || (pixel_bytes % 16) != 0)
+        return fail(JHN_ERR_SHAPE, "need 1<=n_images<=65535, hs>=1, pixel_bytes a multiple of 16 (got %d, %d, %d)", n_images, hs, pixel_bytes);
+    if (((uintptr_t)host_heatmaps | (uintptr_t)device_heatmaps) & 15) return fail(JHN_ERR_ARG, "jhn_pull_heatmap_boxes: tensors must be 16-byte aligned");
+    void *mapped = nullptr;
+    if (cudaHostGetDevicePointer(&mapped, const_cast<void *>(host_heatmaps), 0) != cudaSuccess || !mapped) {
+        cudaGetLastError();
+        return fail(JHN_ERR_ARG, "jhn_pull_heatmap_boxes: host_heatmaps is not pinned, device-mapped host memory (cudaHostAlloc / cudaHostRegister)");
+    }
+    return pull_boxes_launch(mapped, device_heatmaps, boxes, n_images, hs, pixel_bytes, bytes_pulled, (cudaStream_t)stream);
 }
 
 int jhn_ingest_frames(const uint8_t *frames, int N, int H, int W, float *imgs, jhn_stream_t stream)

@@ -93,6 +93,11 @@ int center_locate_launch(const float *hm, int B, int ncam, int Hc, int Wc, int i
 int crop_normalize_launch(const float *imgs, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,
                           const int32_t *valid, const float *mean, const float *std, float *out, cudaStream_t st);
 
+int heatmap_boxes_launch(const float *cam, const float *intr, const float *dist, const float *center3D, const int32_t *centerHM,
+                         int B, int ncam, int hs, int G, float spacing, int32_t *boxes, cudaStream_t st);
+
+int pull_boxes_launch(const void *host_mapped, void *dev, const int32_t *boxes, int n_images, int hs, int pixel_bytes,
+                      unsigned long long *bytes_out, cudaStream_t st);
 // ingest.cu (rows f4 / a11) and head2d.cu (row f2)
 int ingest_frames_launch(const uint8_t *frames, int N, int H, int W, float *out, cudaStream_t st);
 int crop_normalize_u8_launch(const uint8_t *frames, int B, int ncam, int H, int W, int bbox, const int32_t *centerHM,

@@ -743,7 +743,11 @@ int tc_create(jhn_v2v *net, const float *const *tensors, cudaStream_t st)
     JHN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     JHN_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     TcNet *tc = new TcNet();
-    tc->blob = nullptr; tc->max_smem = max_smem;
+    // Leave a sliver of the SM's shared memory unclaimed: every resident CTA costs 1 KB of system-reserved shared memory, so a
+    // convolution CTA sized to the full 227 KB keeps ANY other CTA off its SM — including the 0-byte transfer kernel of the
+    // end-to-end path (jhn_pull_heatmap_boxes), which must run next to these persistent kernels to overlap PCIe with compute.
+    static const int reserve = [] { const char *e = getenv("JHN_SMEM_RESERVE"); return e ? atoi(e) : 3072; }();
+    tc->blob = nullptr; tc->max_smem = max_smem - reserve;
     const char *leg = getenv("JHN_CONV3_LEGACY");
     tc->legacy_k3 = leg && leg[0] == '1';
     net->tc = tc;

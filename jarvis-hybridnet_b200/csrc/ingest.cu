@@ -13,6 +13,8 @@
 //   softplus2_kernel          jarvis/hybridnet/model.py:73,88   heatmap_final = softplus(softplus(v2v))  (the returned volume)
 //   pad_border_kernel         jarvis/hybridnet/model.py:65-66   heatmaps_padded = F.pad(heatmaps, [1,1,1,1])
 // All four are HBM-bound streaming kernels: 16-byte accesses, one pass.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace jhn {
@@ -103,6 +105,60 @@ pad_border_kernel(const float *__restrict__ in, int S, long long n_out, float *_
     const int r = (int)(i - img * hs * hs), y = r / hs, x = r - y * hs;
     const bool inside = y >= 1 && y <= S && x >= 1 && x <= S;
     out[i] = inside ? __ldg(in + (size_t)img * S * S + (size_t)(y - 1) * S + (x - 1)) : 0.f;
+}
+
+// Host -> device transfer of only the pixels the gather reads, executed by the SMs: the channels-last heat maps stay in
+// pinned (device-mapped) host memory and this kernel reads each image's pixel box over PCIe and writes it to the same place
+// of the device tensor.  A copy engine walks a strided (2-D) copy at ~0.16 us per row — 36 GB/s on these 5 KB rows, less
+// than copying the whole tensor contiguously — whereas coalesced 16-byte loads from mapped memory run at link speed for
+// any row length, and the boxes never have to visit the host (jhn_heatmap_boxes leaves them on the device).
+// A SMALL persistent grid (PULL_CTAS CTAs of 128 threads x 32 registers, no shared memory) walks the work items
+// (image, part of its box), 2 loads in flight per thread: ~200 KB in flight cover the link's bandwidth-delay product, and
+// one such CTA fits next to the persistent convolution / gather CTAs (they leave 4096 registers and, with
+// JHN_SMEM_RESERVE, 3 KB of shared memory per SM free), so the transfer of chunk i+1 overlaps the kernels of chunk i
+// without ever keeping a compute CTA off an SM — a grid with one CTA per work item did exactly that.
+constexpr int PULL_THREADS = 128, PULL_SPLIT = 8, PULL_UNROLL = 2, PULL_CTAS = 48;
+__global__ void __launch_bounds__(PULL_THREADS, 16)
+pull_boxes_kernel(const uint4 *__restrict__ host, uint4 *__restrict__ dev, const int4 *__restrict__ boxes, int n_images, int hs,
+                  int units_per_pixel, unsigned long long *__restrict__ bytes_out)
+{
+    for (int w = blockIdx.x; w < n_images * PULL_SPLIT; w += gridDim.x) {
+        const int img = w / PULL_SPLIT, part = w - img * PULL_SPLIT;
+        const int4 bx = __ldg(boxes + img);                           // {x0, y0, -x1, -y1}
+        const int x0 = bx.x, y0 = bx.y, bw = -bx.z - bx.x + 1, bh = -bx.w - bx.y + 1;
+        if (x0 < 0 || y0 < 0 || bw < 1 || bh < 1 || x0 + bw > hs || y0 + bh > hs) continue;  // no box: nothing the gather could read
+        const int row_units = bw * units_per_pixel, pitch_units = hs * units_per_pixel;
+        const int total = row_units * bh;                             // < 2^31: one image
+        const size_t base = (size_t)img * hs * pitch_units + (size_t)y0 * pitch_units + (size_t)x0 * units_per_pixel;
+        const uint4 *src = host + base;
+        uint4 *dst = dev + base;
+        constexpr int stride = PULL_THREADS * PULL_SPLIT;
+        for (int u0 = part * PULL_THREADS + threadIdx.x; u0 < total; u0 += stride * PULL_UNROLL) {
+            uint4 v[PULL_UNROLL];
+            int off[PULL_UNROLL];
+#pragma unroll
+            for (int k = 0; k < PULL_UNROLL; ++k) {
+                const int u = u0 + k * stride;
+                const int r = u / row_units;
+                off[k] = u + r * (pitch_units - row_units);           // r * pitch + (u - r * row_units)
+                if (u < total) v[k] = __ldcs(src + off[k]);           // streaming: each byte crosses the link once
+            }
+#pragma unroll
+            for (int k = 0; k < PULL_UNROLL; ++k)
+                if (u0 + k * stride < total) dst[off[k]] = v[k];
+        }
+        if (bytes_out && part == 0 && threadIdx.x == 0) atomicAdd(bytes_out, (unsigned long long)total * 16ull);
+    }
+}
+
+int pull_boxes_launch(const void *host_mapped, void *dev, const int32_t *boxes, int n_images, int hs, int pixel_bytes,
+                      unsigned long long *bytes_out, cudaStream_t st)
+{
+    JHN_LAUNCH("pull_boxes_kernel", st,
+               pull_boxes_kernel<<<std::min(PULL_CTAS, n_images * PULL_SPLIT), PULL_THREADS, 0, st>>>((const uint4 *)host_mapped, (uint4 *)dev,
+                                                                                                       (const int4 *)boxes, n_images, hs,
+                                                                                                       pixel_bytes / 16, bytes_out));
+    return JHN_OK;
 }
 
 int ingest_frames_launch(const uint8_t *frames, int N, int H, int W, float *out, cudaStream_t st)

@@ -108,7 +108,7 @@ coarse_project_kernel(const float *__restrict__ cam, const float *__restrict__ i
         bb = fminf(fmaxf(bb, loy), hiy);                                                      // :67-68
         bb = __fsub_rn(__fadd_rn(__fsub_rn(bb, chy), fhs), 1.f);
         const size_t o = ((size_t)b * ncam + c) * nc + t;
-        if (live) cab[o] = make_float2(a, bb);               // (x, y) interleaved: one 8-byte access per corner downstream
+        if (live && cab) cab[o] = make_float2(a, bb);        // (x, y) interleaved: one 8-byte access per corner downstream
         if (roi) {
             // pixel box of this camera over the whole voxel grid = min / max over all coarse corners (the fine coordinates
             // are rounded convex combinations of them): warp REDUX -> shared atomics -> one global atomic per block.
@@ -257,6 +257,20 @@ int heatmap_convert_launch(const float *hm, int padded, int B, int ncam, int K, 
     if (dst_format == JHN_HM_F16_CL) return launch_relayout<__half>(a, (__half *)dst, nullptr, st);
     if (dst_format == JHN_HM_BF16_CL) return launch_relayout<__nv_bfloat16>(a, (__nv_bfloat16 *)dst, nullptr, st);
     return fail(JHN_ERR_ARG, "jhn_heatmap_convert: dst_format %d is not a channels-last format", dst_format);
+}
+
+// jhn_heatmap_boxes: only the per-camera pixel boxes of the voxel grid (no coordinate dump): what a host needs to know to
+// upload just the pixels the gather can touch.  boxes: int4 {x0, y0, -x1, -y1} per (frame set, camera).
+int heatmap_boxes_launch(const float *cam, const float *intr, const float *dist, const float *center3D, const int32_t *centerHM,
+                         int B, int ncam, int hs, int G, float spacing, int32_t *boxes, cudaStream_t st)
+{
+    const int h = G / 2;
+    JHN_CUDA(cudaMemsetAsync(boxes, 0x7f, (size_t)B * ncam * sizeof(int4), st));
+    JHN_LAUNCH("coarse_project_kernel", st,
+               coarse_project_kernel<<<dim3(cdiv((long long)h * h * h, 256), B), 256,
+                                       ncam * (CP_PARAMS * sizeof(float) + 4 * sizeof(int)), st>>>(
+                   cam, intr, dist, center3D, centerHM, B, ncam, h, spacing, hs, nullptr, (int *)boxes));
+    return JHN_OK;
 }
 
 constexpr int TS = 8;                                   // voxel tile side

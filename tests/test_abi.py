@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 def test_abi_version(lib):
     from jarvis_hybridnet_b200 import _lib
-    assert lib.jhn_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.jhn_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_shape_validation_without_gpu(lib):

@@ -191,8 +191,8 @@ def test_predict_frames_batched_on_the_real_predictor(tmp_path):
             n = predict3D_frames(acc, read, 5, (cam, intr, dist), path, 12, (1280, 1024), batch=2)
             assert n == 5
             rows = open(path).read().splitlines()
-            assert len(rows) == 5 and rows[4] == rows[1] and rows[0] == rows[3]
-            for i, r in enumerate(ref):
+            assert len(rows) == 5
+            for i, r in [(j, ref[j % 3]) for j in range(5)]:
                 if r is None:
                     assert rows[i] == ",".join(["NaN"] * 92)                       # predict3D.py:93-96
                 else:

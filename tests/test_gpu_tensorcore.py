@@ -96,6 +96,59 @@ def test_forward_host_pipelined_equals_forward():
     assert torch.equal(pts2, pts) and torch.equal(conf2, conf)      # run to run: bit-identical
 
 
+def test_forward_host_uploads_only_the_pixel_boxes():
+    """Channels-last heat maps on the host: forward_host uploads each camera's pixel box of the voxel grid and nothing
+    else (jhn_heatmap_boxes + jhn_upload_heatmap_boxes).  Same bits as uploading whole maps, also when everything
+    outside the boxes is poisoned on the device; the boxes contain every index the reference computes."""
+    import jarvis_hybridnet_b200.synth as S
+    from jarvis_hybridnet_b200 import HybridNet3D, _lib
+    sh = S.SMALL
+    cam, intr, dist = S.make_rig(sh.ncam, 3)
+    sets = [S.make_frameset(sh, cam, intr, dist, s) for s in range(5)]
+    net = HybridNet3D(sh.K, sh.bbox, sh.roi, sh.spacing, S.make_v2v_weights(sh.K, 1, "he"), precision="bf16").to(DEV)
+    rep = lambda a: np.broadcast_to(a[None], (5,) + a.shape).copy()
+    hm = np.stack([s[0] for s in sets])
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
+            (S.to_cl16(hm), np.stack([s[1] for s in sets]), np.stack([s[2] for s in sets]), rep(cam), rep(intr), rep(dist))]
+    full = sum(t.numel() * t.element_size() for t in host)
+    want, h2d_full, _ = net.forward_host(host, chunk=2, roi_upload=None)
+    want = want.clone()
+    assert h2d_full == full
+    res, h2d, d2h = net.forward_host(host, chunk=2)                 # "dma": the boxes by strided copy-engine transfers
+    assert torch.equal(res, want)
+    assert h2d < full and h2d > sum(t.numel() * t.element_size() for t in host[1:])
+    res, h2d_pull, _ = net.forward_host(host, chunk=2, roi_upload="pull")  # boxes read out of mapped host memory by a kernel
+    assert torch.equal(res, want) and h2d_pull == h2d
+    # poison everything on the device, upload the boxes again: the gather must not see the poison
+    for mode in ("dma", "pull"):
+        for slot in net._host["slots"]:
+            slot["dbuf"][0].view(torch.int16).fill_(0x7e00)          # fp16 NaN
+        res, h2d2, _ = net.forward_host(host, chunk=2, roi_upload=mode)
+        assert torch.equal(res, want) and h2d2 == h2d
+    # two steps in flight (double-buffered slots): same results, in order
+    other = [host[0].flip(0).contiguous().pin_memory()] + [t.flip(0).contiguous().pin_memory() for t in host[1:]]
+    a = net.forward_host_async(host, chunk=2)
+    b = net.forward_host_async(other, chunk=2)
+    ra, rb = a.result()[0].clone(), b.result()[0].clone()
+    assert torch.equal(ra, want)
+    assert torch.allclose(rb.flip(0), want, rtol=0, atol=5e-3)      # frame sets in another batch position: fp32 re-association only
+    # the boxes bound the reference's indices (the fp32 path dumps them: repro_layer.py:82-83)
+    from jarvis_hybridnet_b200 import ReprojectionLayer
+    boxes = net._host["slots"][1]["hboxes"].numpy()                  # pinned copy of jhn_heatmap_boxes' output (slot of step `a`)
+    devt = [t.to(DEV) for t in host]
+    from test_host import cfg_of
+    layer = ReprojectionLayer(cfg_of(sh), sh.ncam, precision="fp32")
+    _, idx = layer.forward_batched(torch.from_numpy(hm).to(DEV), *devt[1:], want_index=True)
+    idx = idx.cpu().numpy().reshape(5, sh.ncam, -1)
+    hs = sh.bbox // 2 + 2
+    for b in range(5):
+        for c in range(sh.ncam):
+            x, y = idx[b, c] % hs, idx[b, c] // hs
+            x0, y0, x1, y1 = boxes[b, c, 0], boxes[b, c, 1], -boxes[b, c, 2], -boxes[b, c, 3]
+            assert x.min() >= x0 and x.max() <= x1 and y.min() >= y0 and y.max() <= y1
+            assert x1 - x0 <= (x.max() - x.min()) + 2 and y1 - y0 <= (y.max() - y.min()) + 2      # and they are tight
+
+
 @pytest.mark.parametrize("name", V2V_CASES)
 def test_v2v_bf16_vs_oracle(oracle, name):
     sh, x, g = load_case(name)
