@@ -74,6 +74,14 @@ tc_conv3_kernel(const C3Launch L)
     constexpr int CW = NOUT / EW;                      // output channels per epilogue warp
     constexpr int W_BYTES = 9 * KC * N3 * 16;
     static_assert(NOUT % 16 == 0 && N3 <= 256, "stacked N must be a legal tcgen05 N");
+#ifndef C3_ACC_BUFS
+#define C3_ACC_BUFS 2
+#endif
+    // accumulator buffers in TMEM (512 columns): three when they fit (N3 <= 160), so that the MMAs run up to two tiles ahead
+    // of the epilogue; else two
+    constexpr int ACC_STRIDE = (N3 + 31) / 32 * 32;
+    constexpr int NB = (C3_ACC_BUFS >= 3 && 3 * ACC_STRIDE <= 512) ? 3 : 2;
+    constexpr int ACC_COLS = NB == 3 ? ACC_STRIDE : 256;
     static_assert(NOUT % (8 * EW) == 0, "channels per epilogue warp must be whole 8-channel chunks");
 
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -86,7 +94,7 @@ tc_conv3_kernel(const C3Launch L)
     float *xch = reinterpret_cast<float *>(ring + (size_t)L.NS * slot_bytes);     // [2][4][2][NOUT]
     float *bias_s = xch + 2 * 4 * 2 * NOUT;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + NOUT);
-    uint64_t *full = bars, *empty = bars + C3_MAX_SLOTS, *tfull = bars + 2 * C3_MAX_SLOTS, *tempty = tfull + 2, *wbar = tempty + 2;
+    uint64_t *full = bars, *empty = bars + C3_MAX_SLOTS, *tfull = bars + 2 * C3_MAX_SLOTS, *tempty = tfull + 3, *wbar = tempty + 3;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(wbar + 1);
 
     const int t_begin = (int)((long long)L.total_tiles * blockIdx.x / gridDim.x);
@@ -94,7 +102,7 @@ tc_conv3_kernel(const C3Launch L)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < L.NS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * EW); }
+        for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * EW); }
         mbar_init(smem_u32(wbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -152,23 +160,32 @@ tc_conv3_kernel(const C3Launch L)
             const uint32_t w_units = smem_u32(w_smem) >> 4, ring_units = smem_u32(ring) >> 4;
             const uint32_t slot_units = (uint32_t)slot_bytes >> 4;
             mbar_wait(smem_u32(wbar), 0);
-            int k = 0;                                                         // plane boxes requested so far
+            // ring position of the oldest plane box of the current tile (box index k - 3, k = boxes requested so far), kept as
+            // (slot, wrap parity) so that the issue path has no integer division (two I2F-based divisions per plane sat in it)
+            int s0 = 0; uint32_t w0 = 0;
+            bool first = true;
             int ab = 0; uint32_t aphase = 0;
             int z = t_begin % D;
             for (int t = t_begin; t < t_end; ++t) {
                 const bool fresh = (t == t_begin) || (z == 0);
                 const bool last = (t + 1 == t_end) || (z + 1 == D);           // the column ends with this tile
-                k += fresh ? 3 : 1;
+                if (!first) { s0 += fresh ? 3 : 1; if (s0 >= L.NS) { s0 -= L.NS; w0 ^= 1u; } }
+                first = false;
                 mbar_wait(smem_u32(tempty + ab), aphase ^ 1);
+#ifndef C3_NO_FENCE
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * 256);
+#endif
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC_COLS);
                 uint32_t acc = 0;
 #pragma unroll 1
                 for (int dz = 0; dz < 3; ++dz) {
-                    const int i = k - 3 + dz, slot = i % L.NS;
+                    int slot = s0 + dz; uint32_t wrap = w0;
+                    if (slot >= L.NS) { slot -= L.NS; wrap ^= 1u; }
                     if (fresh || dz == 2) {
-                        mbar_wait(smem_u32(full + slot), (uint32_t)(i / L.NS) & 1u);
+                        mbar_wait(smem_u32(full + slot), wrap);
+#if !defined(C3_NO_FENCE) && !defined(C3_NO_FULL_FENCE)
                         tc_fence_after();
+#endif
                     }
                     const uint32_t a0 = ring_units + (uint32_t)slot * slot_units;
                     const uint32_t b0 = w_units + (uint32_t)(dz * 3 * KC * N3);
@@ -186,7 +203,7 @@ tc_conv3_kernel(const C3Launch L)
                     if (dz == 0 || last) tc_commit(smem_u32(empty + slot));   // plane box dead once these MMAs retire
                 }
                 tc_commit(smem_u32(tfull + ab));
-                if (++ab == 2) { ab = 0; aphase ^= 1; }
+                if (++ab == NB) { ab = 0; aphase ^= 1; }
                 if (++z == D) z = 0;
             }
         }
@@ -241,12 +258,12 @@ tc_conv3_kernel(const C3Launch L)
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty + ab));
             optr += plane_stride;
-            if (++ab == 2) { ab = 0; aphase ^= 1; }
+            if (++ab == NB) { ab = 0; aphase ^= 1; }
             if (++z == D) { z = 0; column_changed = true; if (++pt == L.NT) { pt = 0; ++b; } }
             continue;
 #endif
             float o[CW];
-            const uint32_t taddr = taddr0 + (uint32_t)(ab * 256);
+            const uint32_t taddr = taddr0 + (uint32_t)(ab * ACC_COLS);
 #pragma unroll
             for (int pc = 0; pc < CW / 8; ++pc) {
                 uint32_t d0[8], d1[8], d2[8];
@@ -303,7 +320,7 @@ tc_conv3_kernel(const C3Launch L)
                 }
             }
             optr += plane_stride;
-            if (++ab == 2) { ab = 0; aphase ^= 1; }
+            if (++ab == NB) { ab = 0; aphase ^= 1; }
             if (++z == D) {
                 z = 0; column_changed = true;
                 if (++pt == L.NT) { pt = 0; ++b; }
@@ -336,7 +353,7 @@ __global__ void c3_pack_weights_kernel(const float *__restrict__ src, __nv_bfloa
     dst[e] = __float2bfloat16_rn(v);
 }
 
-static size_t c3_tail_bytes(int NOUT) { return (size_t)(2 * 4 * 2 * NOUT + NOUT) * 4 + (2 * C3_MAX_SLOTS + 5) * 8 + 16; }
+static size_t c3_tail_bytes(int NOUT) { return (size_t)(2 * 4 * 2 * NOUT + NOUT) * 4 + (2 * C3_MAX_SLOTS + 7) * 8 + 16; }
 
 size_t c3_weight_bytes(int NOUT) { return (size_t)9 * (NOUT / 8) * 3 * NOUT * 16; }
 

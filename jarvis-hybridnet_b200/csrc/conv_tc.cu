@@ -459,9 +459,18 @@ int tc_zero_border_launch(void *tensor, int chunks_total, int D, cudaStream_t st
 // optionally also writes the parity-split copy the following stride-2 convolution reads.  HBM-bound: one block
 // per (sample, 8-channel chunk, z-plane) walks the plane's contiguous run of padded positions with 16-byte
 // accesses; the 8 (mean, rstd) pairs are computed once per block, pad columns are skipped (they stay zero).
-constexpr int NORM_THREADS = 256, NORM_UNROLL = 3, NORM_ZB = 4;      // NORM_ZB z-planes per block: the statistics prologue is paid once per 4 planes
+#ifndef NORM_UNROLL_V
+#define NORM_UNROLL_V 3
+#endif
+#ifndef NORM_MINB
+#define NORM_MINB 1
+#endif
+#ifndef NORM_ZB_V
+#define NORM_ZB_V 4
+#endif
+constexpr int NORM_THREADS = 256, NORM_UNROLL = NORM_UNROLL_V, NORM_ZB = NORM_ZB_V;      // NORM_ZB z-planes per block: the statistics prologue is paid once per 4 planes
 template <bool HAS_RES, bool HAS_POST, bool HAS_PS>
-__global__ void __launch_bounds__(NORM_THREADS)
+__global__ void __launch_bounds__(NORM_THREADS, NORM_MINB)
 tc_norm_act_kernel(uint4 *__restrict__ x, const StatPart stats, const uint4 *__restrict__ residual,
                    const uint4 *__restrict__ post_add, uint4 *__restrict__ ps_out, int relu, int D, int CJ, int NOUT,
                    float inv_count, float eps, uint32_t wp_magic)

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int mode, int 
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+    for (int i = threadIdx.x; i < 224 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
     if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
@@ -43,13 +43,46 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int mode, int 
     if (threadIdx.x == 0) {
         const int M = mode == 2 ? 64 : 128;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 128 * 1024;
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + (mode >= 4 ? 100 * 1024 : 128 * 1024);
         const uint32_t layout = mode == 3 ? 2u : 0u;
         const uint32_t lboA = mode == 3 ? 16 : (uint32_t)lbo_a, sboA = mode == 3 ? 1024 : 128;
         const uint32_t lboB = mode == 3 ? 16 : (uint32_t)N * 16, sboB = mode == 3 ? 1024 : 128;
         // descriptors precomputed: 4 different A start rows (like taps), issue loop is 4 bare MMAs
         uint64_t ad[4], bd = desc(b0, lboB, sboB, layout);
         for (int i = 0; i < 4; ++i) ad[i] = desc(a0 + (mode == 3 ? 0u : (uint32_t)(i * 48)), lboA, sboA, layout);
+        if (mode >= 4) {
+            // conv3_tc.cu's exact operand stream: per tile 27 MMAs = 3 planes x 3 dy x 3 K-steps, A = plane box (PB = 204
+            // positions, KC = 6 chunks) shifted by dy * 38 rows, B = a different 144-column weight slab per MMA (124 KB
+            // resident).  mode 4: B as in the kernel; mode 5: the same B slab for every MMA; mode 6: A unshifted (dy * 40).
+            const int PB = 204, KC = 6, N3 = 144, Wp = mode == 6 ? 40 : 38;
+            const uint32_t w_units = b0 >> 4, ring_units = a0 >> 4, slot_units = KC * PB;
+            const uint64_t hi_c = (uint64_t)(8u | (1u << 14)) << 32;
+            const uint32_t lbo_a2 = (uint32_t)PB << 16, lbo_b2 = (uint32_t)N3 << 16;
+            const uint32_t id = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            long long t0 = clock64();
+            for (int it = 0; it < iters; it += 27) {
+                const uint32_t d = tmem + (((it / 27) & 1) ? 256u : 0u);
+                uint32_t acc = 0;
+#pragma unroll 1
+                for (int dz = 0; dz < 3; ++dz) {
+                    const uint32_t a00 = ring_units + (uint32_t)(((it / 27) + dz) % 5) * slot_units;
+                    const uint32_t b00 = w_units + (mode == 5 ? 0u : (uint32_t)(dz * 3 * KC * N3));
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int kc = 0; kc < KC; kc += 2) {
+                            const uint32_t a_lo = lbo_a2 | (a00 + (uint32_t)(dy * Wp + kc * PB));
+                            const uint32_t b_lo = lbo_b2 | (b00 + (mode == 5 ? 0u : (uint32_t)((dy * KC + kc) * N3)));
+                            mma(d, hi_c | (uint64_t)a_lo, hi_c | (uint64_t)b_lo, id, acc);
+                            acc = 1;
+                        }
+                }
+            }
+            tc_commit(smem_u32(&bar));
+            mbar_wait(smem_u32(&bar), 0);
+            long long t1 = clock64();
+            if (blockIdx.x == 0) *out = t1 - t0;
+        } else {
         const uint32_t d0 = tmem, d1 = tmem + (mode == 1 ? 256u : 0u);
         mma(d0, ad[0], bd, idesc, 0);
         mma(d1, ad[1], bd, idesc, 0);
@@ -64,6 +97,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int mode, int 
         mbar_wait(smem_u32(&bar), 0);
         long long t1 = clock64();
         if (blockIdx.x == 0) *out = t1 - t0;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -74,7 +108,7 @@ int main()
 {
     long long *d_out, h;
     cudaMalloc(&d_out, 8);
-    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     const int iters = 4096;
     const int Ns[] = {16, 32, 48, 64, 80, 96, 112, 128, 144, 160, 176, 192, 256};
     printf("grid mode lboA N cycles_per_mma ideal(=N/2)\n");
@@ -83,12 +117,22 @@ int main()
             for (int lbo : {3296, 2048})
                 for (int N : Ns) {
                     if (mode != 0 && lbo != 3296) continue;
-                    bench<<<grid, 128, 200 * 1024>>>(N, 64, mode, lbo, d_out);
-                    bench<<<grid, 128, 200 * 1024>>>(N, iters, mode, lbo, d_out);
+                    bench<<<grid, 128, 224 * 1024>>>(N, 64, mode, lbo, d_out);
+                    bench<<<grid, 128, 224 * 1024>>>(N, iters, mode, lbo, d_out);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                     cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
                     printf("%d %d %d %d %.1f %.1f\n", grid, mode, lbo, N, (double)h / iters, N / 2.0);
                 }
+    for (int grid : {1, 148})
+        for (int mode : {4, 5, 6}) {
+            const int it27 = 27 * 152;
+            bench<<<grid, 128, 224 * 1024>>>(144, 54, mode, 0, d_out);
+            bench<<<grid, 128, 224 * 1024>>>(144, it27, mode, 0, d_out);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+            cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
+            printf("conv3-like grid %d mode %d: %.1f cycles per MMA (27 per tile)\n", grid, mode, (double)h / it27);
+        }
     return 0;
 }
