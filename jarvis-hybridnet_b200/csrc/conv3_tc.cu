@@ -18,10 +18,10 @@
 // are a sliding window over a ring of plane boxes in shared memory: after the first tile of a column every
 // tile fetches ONE new plane box (KC contiguous TMA bulk copies) instead of three.
 //
-// Roles (320 threads, one persistent CTA per SM):
+// Roles (one persistent CTA per SM):
 //     warp 0      TMA producer (one elected lane): weights once (resident, 124 KB for C = 48), plane boxes
-//     warp 1      TMEM allocator + MMA issuer (one elected lane), descriptors formed by register arithmetic
-//     warps 2-9   epilogue: two warps per TMEM lane quadrant, each owning half of the output channels:
+//     warps 1-2   MMA issuers (one elected lane each, alternate tiles; warp 1 also allocates TMEM)
+//     warps 3-    epilogue: two warps per TMEM lane quadrant, each owning half of the output channels:
 //                 tcgen05.ld -> shuffle-combine -> bias -> pad mask -> bf16 store, and the per-channel
 //                 sum / sum-of-squares of the following InstanceNorm accumulated in registers across tiles
 //                 (one atomicAdd per channel and warp when the CTA's range leaves a sample).
@@ -65,10 +65,10 @@ __device__ __forceinline__ void c3_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, 
 
 // EW = epilogue warps per TMEM lane quadrant; each owns NOUT / EW output channels
 template <int NOUT, int EW>
-__global__ void __launch_bounds__(64 + 128 * EW, 1)
+__global__ void __launch_bounds__(96 + 128 * EW, 1)
 tc_conv3_kernel(const C3Launch L)
 {
-    constexpr int C3_THREADS = 64 + 128 * EW;
+    constexpr int C3_THREADS = 96 + 128 * EW;
     constexpr int KC = NOUT / 8;                       // 8-channel chunks of the input (Cin == Cout == NOUT)
     constexpr int N3 = 3 * NOUT;                       // MMA N: three x-taps stacked
     constexpr int CW = NOUT / EW;                      // output channels per epilogue warp
@@ -80,7 +80,7 @@ tc_conv3_kernel(const C3Launch L)
     // accumulator buffers in TMEM (512 columns): three when they fit (N3 <= 160), so that the MMAs run up to two tiles ahead
     // of the epilogue; else two
     constexpr int ACC_STRIDE = (N3 + 31) / 32 * 32;
-    constexpr int NB = (C3_ACC_BUFS >= 3 && 3 * ACC_STRIDE <= 512) ? 3 : 2;
+    constexpr int NB = 2;                              // one accumulator buffer per issuing thread
     constexpr int ACC_COLS = NB == 3 ? ACC_STRIDE : 256;
     static_assert(NOUT % (8 * EW) == 0, "channels per epilogue warp must be whole 8-channel chunks");
 
@@ -101,7 +101,7 @@ tc_conv3_kernel(const C3Launch L)
     const int t_end = (int)((long long)L.total_tiles * (blockIdx.x + 1) / gridDim.x);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < L.NS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
+        for (int i = 0; i < L.NS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 3); }
         for (int i = 0; i < NB; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * EW); }
         mbar_init(smem_u32(wbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -151,66 +151,89 @@ tc_conv3_kernel(const C3Launch L)
                 if (++z == D) { z = 0; ++u; }
             }
         }
-    } else if (warp == 1) {
-        // =================================== MMA issuer ======================================
+    } else if (warp <= 2) {
+        // =================================== MMA issuers =====================================
+        // TWO issuing threads (warps 1 and 2, on different schedulers) take alternate tiles of the CTA's range, each into the
+        // accumulator buffer of its own.  One thread needs ~100 cycles of instruction time per N = 144 MMA (descriptor
+        // arithmetic, R2UR, barrier waits; the tensor pipe needs 72 and tools/umma_bench.cu reaches that only with a bare
+        // issue loop), and the pipe queues too few MMAs to hide a prep block: with two threads each has two tile times per tile.
+        // MMAs of different tiles may interleave in the pipe: they accumulate into different TMEM buffers.
+        // A plane box is read by up to three consecutive tiles (dz = 2, 1, 0), i.e. by both threads: its empty barrier
+        // counts three arrivals, one tcgen05.commit per reading tile; at the ends of a column segment, where a plane has
+        // fewer readers, the last reader adds the missing arrivals.
         if (elect_one()) {
+            const int me = warp - 1;
             const uint32_t idesc = umma_idesc_bf16(N3);
             const uint64_t hi_c = (uint64_t)(8u | (1u << 14)) << 32;           // SBO = 128 B, descriptor version 1
             const uint32_t lbo_a = (uint32_t)L.PB << 16, lbo_b = (uint32_t)N3 << 16;   // K-chunk strides, 16-byte units
             const uint32_t w_units = smem_u32(w_smem) >> 4, ring_units = smem_u32(ring) >> 4;
             const uint32_t slot_units = (uint32_t)slot_bytes >> 4;
             mbar_wait(smem_u32(wbar), 0);
-            // ring position of the oldest plane box of the current tile (box index k - 3, k = boxes requested so far), kept as
-            // (slot, wrap parity) so that the issue path has no integer division (two I2F-based divisions per plane sat in it)
+            // ring position of the oldest plane box of the current tile as (slot, wrap parity): no integer division on the issue path
             int s0 = 0; uint32_t w0 = 0;
-            bool first = true;
-            int ab = 0; uint32_t aphase = 0;
+            uint32_t aphase = 0;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(me * ACC_COLS);
             int z = t_begin % D;
+            int seg_i = 0;                                                     // index of the tile inside its column segment
             for (int t = t_begin; t < t_end; ++t) {
                 const bool fresh = (t == t_begin) || (z == 0);
-                const bool last = (t + 1 == t_end) || (z + 1 == D);           // the column ends with this tile
-                if (!first) { s0 += fresh ? 3 : 1; if (s0 >= L.NS) { s0 -= L.NS; w0 ^= 1u; } }
-                first = false;
-                mbar_wait(smem_u32(tempty + ab), aphase ^ 1);
-#ifndef C3_NO_FENCE
-                tc_fence_after();
-#endif
-                const uint32_t d_tmem = tmem_base + (uint32_t)(ab * ACC_COLS);
-                uint32_t acc = 0;
-#pragma unroll 1
-                for (int dz = 0; dz < 3; ++dz) {
-                    int slot = s0 + dz; uint32_t wrap = w0;
-                    if (slot >= L.NS) { slot -= L.NS; wrap ^= 1u; }
-                    if (fresh || dz == 2) {
-                        mbar_wait(smem_u32(full + slot), wrap);
-#if !defined(C3_NO_FENCE) && !defined(C3_NO_FULL_FENCE)
-                        tc_fence_after();
-#endif
+                const bool last = (t + 1 == t_end) || (z + 1 == D);           // the column segment ends with this tile
+                if (t != t_begin) { s0 += fresh ? 3 : 1; if (s0 >= L.NS) { s0 -= L.NS; w0 ^= 1u; } }
+                if (fresh) seg_i = 0;
+                if (((t - t_begin) & 1) == me) {
+                    mbar_wait(smem_u32(tempty + me), aphase ^ 1);
+                    tc_fence_after();
+                    aphase ^= 1;
+                    uint32_t acc = 0;
+                    // all three planes are waited for up front and the 27 MMAs of the tile are one straight-line block: the
+                    // descriptor arithmetic of the whole tile runs while the OTHER thread's MMAs execute, and nothing but
+                    // UTCHMMA / R2UR sits between this tile's MMAs (a prep block per plane left the pipe idle three times a tile)
+                    int slot[3];
+#pragma unroll
+                    for (int dz = 0; dz < 3; ++dz) {
+                        slot[dz] = s0 + dz; uint32_t wrap = w0;
+                        if (slot[dz] >= L.NS) { slot[dz] -= L.NS; wrap ^= 1u; }
+                        // every plane is waited for by the thread that reads it: the other thread observed the planes this tile
+                        // shares with its predecessor, this one may not have (second tile of a segment)
+                        mbar_wait(smem_u32(full + slot[dz]), wrap);
                     }
-                    const uint32_t a0 = ring_units + (uint32_t)slot * slot_units;
-                    const uint32_t b0 = w_units + (uint32_t)(dz * 3 * KC * N3);
+                    tc_fence_after();
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy)
+                    for (int dz = 0; dz < 3; ++dz) {
+                        const uint32_t a0 = ring_units + (uint32_t)slot[dz] * slot_units;
+                        const uint32_t b0 = w_units + (uint32_t)(dz * 3 * KC * N3);
 #pragma unroll
-                        for (int kc = 0; kc < KC; kc += 2) {
-                            const uint32_t a_lo = lbo_a | (a0 + (uint32_t)(dy * Wp + kc * L.PB));
-                            const uint32_t b_lo = lbo_b | (b0 + (uint32_t)((dy * KC + kc) * N3));
+                        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                            for (int kc = 0; kc < KC; kc += 2) {
+                                const uint32_t a_lo = lbo_a | (a0 + (uint32_t)(dy * Wp + kc * L.PB));
+                                const uint32_t b_lo = lbo_b | (b0 + (uint32_t)((dy * KC + kc) * N3));
 #ifndef C3_DBG_NO_MMA
-                            tc_mma_bf16(d_tmem, hi_c | (uint64_t)a_lo, hi_c | (uint64_t)b_lo, idesc, acc);
+                                tc_mma_bf16(d_tmem, hi_c | (uint64_t)a_lo, hi_c | (uint64_t)b_lo, idesc, acc);
 #endif
-                            acc = 1;
+                                acc = 1;
+                            }
+                        const uint32_t eb = smem_u32(empty + slot[dz]);
+                        tc_commit(eb);                                         // this tile's read of the plane box
+                        if (dz == 0 || last) {
+                            // last reader of plane j = seg_i + dz of the segment: readers are the tiles max(0, j-2) .. min(n-1, j);
+                            // n is not known before the segment ends, but "last" says whether this tile is n - 1
+                            const int j = seg_i + dz;
+                            const int first_reader = j - 2 > 0 ? j - 2 : 0;
+                            const int readers = seg_i - first_reader + 1;      // this tile is the last reader
+                            for (int m = readers; m < 3; ++m) mbar_arrive(eb);
                         }
-                    if (dz == 0 || last) tc_commit(smem_u32(empty + slot));   // plane box dead once these MMAs retire
+                    }
+                    tc_commit(smem_u32(tfull + me));
                 }
-                tc_commit(smem_u32(tfull + ab));
-                if (++ab == NB) { ab = 0; aphase ^= 1; }
+                ++seg_i;
                 if (++z == D) z = 0;
             }
         }
     } else {
         // =================================== epilogue warps =================================
         const int q = warp & 3;                                                // TMEM lane quadrant
-        const int part = (warp - 2) >> 2;                                      // which slice of the channels
+        const int part = (warp - 3) >> 2;                                      // which slice of the channels
         const int row = q * 32 + lane;
         const int c_base = part * CW;
         float s1[CW], s2[CW], bias_r[CW];
@@ -393,7 +416,7 @@ static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st
         JHN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<NOUT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured = true; configured_dev = dev;
     }
-    JHN_LAUNCH("tc_conv3_stacked", st, tc_conv3_kernel<NOUT, EW><<<grid, 64 + 128 * EW, smem, st>>>(L));
+    JHN_LAUNCH("tc_conv3_stacked", st, tc_conv3_kernel<NOUT, EW><<<grid, 96 + 128 * EW, smem, st>>>(L));
     return JHN_OK;
 }
 

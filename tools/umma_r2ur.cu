@@ -27,11 +27,11 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int mode, int 
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
-    __shared__ uint64_t bars2[8];
+    __shared__ volatile uint32_t zero_s[4];
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 224 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0;
-    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars2[i]), 1); mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x == 0) { zero_s[0] = 0; zero_s[1] = 0; mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -55,40 +55,35 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, int mode, int 
             // conv3_tc.cu's exact operand stream: per tile 27 MMAs = 3 planes x 3 dy x 3 K-steps, A = plane box (PB = 204
             // positions, KC = 6 chunks) shifted by dy * 38 rows, B = a different 144-column weight slab per MMA (124 KB
             // resident).  mode 4: B as in the kernel; mode 5: the same B slab for every MMA; mode 6: A unshifted (dy * 40).
-            const int PB = 204, KC = 6, N3 = 144, Wp = mode == 6 ? 40 : 38;   // modes 7-9: mode 4 + the kernel's commits / barrier waits
+            const int PB = 204, KC = 6, N3 = 144, Wp = 38;
             const uint32_t w_units = b0 >> 4, ring_units = a0 >> 4, slot_units = KC * PB;
             const uint64_t hi_c = (uint64_t)(8u | (1u << 14)) << 32;
             const uint32_t lbo_a2 = (uint32_t)PB << 16, lbo_b2 = (uint32_t)N3 << 16;
             const uint32_t id = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N3 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             long long t0 = clock64();
-            const int base_mode = mode >= 7 ? 4 : mode;
             for (int it = 0; it < iters; it += 27) {
-                const int tile = it / 27;
-                const uint32_t d = tmem + ((tile & 1) ? 256u : 0u);
+                const uint32_t d = tmem + (((it / 27) & 1) ? 256u : 0u);
                 uint32_t acc = 0;
-                if (mode >= 8 && tile >= 2) {                          // accumulator buffer free? (completed two tiles ago)
-                    mbar_wait(smem_u32(&bars2[tile & 1]), (uint32_t)((tile >> 1) - 1) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
+                uint32_t vt = 0;
+                if (mode == 9) vt = zero_s[0];
 #pragma unroll 1
                 for (int dz = 0; dz < 3; ++dz) {
-                    const uint32_t a00 = ring_units + (uint32_t)(((it / 27) + dz) % 5) * slot_units;
-                    const uint32_t b00 = w_units + (base_mode == 5 ? 0u : (uint32_t)(dz * 3 * KC * N3));
+                    uint32_t vg = vt;
+                    if (mode == 8) vg = zero_s[0];
+                    const uint32_t a00 = ring_units + (uint32_t)(((it / 27) + dz) % 5) * slot_units + vg;
+                    const uint32_t b00 = w_units + (false ? 0u : (uint32_t)(dz * 3 * KC * N3));
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                         for (int kc = 0; kc < KC; kc += 2) {
-                            const uint32_t a_lo = lbo_a2 | (a00 + (uint32_t)(dy * Wp + kc * PB));
-                            const uint32_t b_lo = lbo_b2 | (b00 + (base_mode == 5 ? 0u : (uint32_t)((dy * KC + kc) * N3)));
+                            uint32_t vm = 0;
+                            if (mode == 7) vm = zero_s[0];
+                            const uint32_t a_lo = lbo_a2 | (a00 + vm + (uint32_t)(dy * Wp + kc * PB));
+                            const uint32_t b_lo = lbo_b2 | (b00 + (false ? 0u : (uint32_t)((dy * KC + kc) * N3)));
                             mma(d, hi_c | (uint64_t)a_lo, hi_c | (uint64_t)b_lo, id, acc);
                             acc = 1;
                         }
-                    if (mode >= 7 && dz == 0) tc_commit(smem_u32(&bars2[2 + (tile % 5)]));      // "plane box dead" commit
-                    if (mode >= 9 && dz == 2) {                        // a wait that is already satisfied (like the full barrier of a landed box)
-                        if (tile >= 1) mbar_wait(smem_u32(&bars2[2 + ((tile - 1) % 5)]), (uint32_t)((tile - 1) / 5) & 1u);   // committed one tile ago
-                    }
                 }
-                if (mode >= 7) tc_commit(smem_u32(&bars2[tile & 1]));  // "accumulator ready" commit
             }
             tc_commit(smem_u32(&bar));
             mbar_wait(smem_u32(&bar), 0);
@@ -122,10 +117,10 @@ int main()
     cudaMalloc(&d_out, 8);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     const int iters = 4096;
-    const int Ns[] = {16, 32, 48, 64, 80, 96, 112, 128, 144, 160, 176, 192, 256};
+    const int Ns[] = {144};
     printf("grid mode lboA N cycles_per_mma ideal(=N/2)\n");
-    for (int grid : {1, 148})
-        for (int mode : {0, 1, 2, 3})
+    for (int grid : {148})
+        for (int mode : {0})
             for (int lbo : {3296, 2048})
                 for (int N : Ns) {
                     if (mode != 0 && lbo != 3296) continue;
