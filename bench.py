@@ -609,16 +609,17 @@ def main():
     # ---- end to end through the public API with host buffers: pinned host tensors in, [B,K,4] back in pinned memory.
     # On the bf16 path the heat maps cross PCIe in the gather-native fp16 channels-last form (9.7 MB instead of 18.1 MB per
     # frame set at the Example shape); everything else is the reference's fp32 / int32 tensors. --------------------------
+    e2e_chunk = int(os.environ.get("JHN_E2E_CHUNK", "8"))
     # Steps are pipelined two deep, as a prediction loop with a prefetching loader runs them: step i+1 is submitted
     # (forward_host_async: its uploads queue behind step i's on the copy stream) before step i's result is collected, so the
     # link stays busy while step i computes.  Every step uploads its own inputs and downloads its own result inside the region.
     for i in range(max(min(W, 3), 2)):
-        net.forward_host(host_cl[i % n_pool])
+        net.forward_host(host_cl[i % n_pool], chunk=e2e_chunk)
     barrier()
     t0 = time.perf_counter()
-    pending = net.forward_host_async(host_cl[0])
+    pending = net.forward_host_async(host_cl[0], chunk=e2e_chunk)
     for i in range(1, K_steps + 1):
-        nxt = net.forward_host_async(host_cl[i % n_pool]) if i < K_steps else None
+        nxt = net.forward_host_async(host_cl[i % n_pool], chunk=e2e_chunk) if i < K_steps else None
         res, h2d, d2h = pending.result()
         pending = nxt
     torch.cuda.synchronize()
