@@ -25,6 +25,8 @@
 //                 tcgen05.ld -> shuffle-combine -> bias -> pad mask -> bf16 store, and the per-channel
 //                 sum / sum-of-squares of the following InstanceNorm accumulated in registers across tiles
 //                 (one atomicAdd per channel and warp when the CTA's range leaves a sample).
+#include <atomic>
+
 #include "tc_ptx.cuh"
 #include "v2v.cuh"
 
@@ -406,15 +408,16 @@ int c3_pack(const float *src, __nv_bfloat16 *dst, int cout, int cin, int NOUT, c
 template <int NOUT, int EW>
 static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st)
 {
-    static bool configured = false;                                            // per instantiation; attribute is per device, set on first use
-    static int configured_dev = -1;
+    // the attribute is per (function, device): one bit per device, set on first use, safe from any thread
+    static std::atomic<unsigned long long> configured{0ull};
     int dev = 0;
     JHN_CUDA(cudaGetDevice(&dev));
-    if (!configured || configured_dev != dev) {
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
         int max_smem = 0;
         JHN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         JHN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<NOUT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        configured = true; configured_dev = dev;
+        configured.fetch_or(bit, std::memory_order_release);
     }
     JHN_LAUNCH("tc_conv3_stacked", st, tc_conv3_kernel<NOUT, EW><<<grid, 96 + 128 * EW, smem, st>>>(L));
     return JHN_OK;

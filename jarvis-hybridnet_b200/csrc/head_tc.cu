@@ -14,6 +14,8 @@
 //                 are bit-identical from run to run), the maxima are order-independent atomicMax.
 // The argmax is an atomicMax on a 64-bit key (order-preserving bits of the raw value, ~flat index), i.e. the first
 // flat index of the maximum, independent of scheduling.
+#include <atomic>
+
 #include "tc_ptx.cuh"
 #include "v2v.cuh"
 
@@ -279,12 +281,13 @@ int head_centroid_launch(const void *in, const __nv_bfloat16 *w, const float *bi
     L.NS = ns;
     const size_t smem = head_smem(L.KC, L.NOUT, ns);
     JHN_CUDA(cudaMemsetAsync((char *)acc + head_sum_bytes(B, K), 0, head_acc_bytes(B, K) - head_sum_bytes(B, K), st));   // the two maxima
-    static int configured_dev = -1;
+    static std::atomic<unsigned long long> configured{0ull};          // one bit per device
     int dev = 0;
     JHN_CUDA(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
         JHN_CUDA(cudaFuncSetAttribute(tc_head_centroid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        configured_dev = dev;
+        configured.fetch_or(bit, std::memory_order_release);
     }
     const int grid = L.total_tiles < sms ? L.total_tiles : sms;
     JHN_LAUNCH("tc_head_centroid_kernel", st, tc_head_centroid_kernel<<<grid, HD_THREADS, smem, st>>>(L));
