@@ -8,7 +8,7 @@ timeout -s KILL 600 python bench.py --impl reference > gpurun_out/${TAG}_bench_r
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --no-cpu-baseline --no-latency --no-extras --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu_b.log 2>&1
 # one full forward (27 launches) of the resident path: skip the weight packing + warm-up launches
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"coarse_project|relayout|gather_stream|tc_|centroid_finalize" -s 140 -c 27 \
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"coarse_project|relayout_pixel|gather_stream|tc_conv|tc_norm|tc_head|tc_zero|centroid_finalize" -s 29 -c 27 \
     -o gpurun_out/${TAG}_full -f python bench.py --no-cpu-baseline --no-latency --no-extras --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu_f.log 2>&1
 python - <<P
 import json
