@@ -244,7 +244,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
             int slot = slot0; uint32_t phase = 0;
             int ab = pipe; uint32_t aphase = 0;                      // npipe > 1: issuer r owns accumulator buffer r; one pipeline: it alternates between two
             for (int t = t_begin + pipe; pipe < npipe && t < t_end; t += npipe) {
-                const uint32_t tile_b = P.tile_taps > 1 ? (uint32_t)(t % P.tile_taps) * tap_units : 0u;
+                const uint32_t tile_b = P.tile_taps > 1 ? (uint32_t)(t & (P.tile_taps - 1)) * tap_units : 0u;   // tile_taps is 1 or 8 (build_program)
                 mbar_wait(smem_u32(tempty + ab), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(ab * 2 * P.NOUT);
@@ -255,19 +255,30 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
                     const uint2 *dl = desc_list + slot * n_mma;
                     const int e1 = stage_first[s + 1];
                     int e = stage_first[s];
+                    // descriptor pairs are fetched one step AHEAD of the MMAs that use them: the MMA wrapper is a compiler-level
+                    // memory barrier, so a load placed after it would start only once the previous MMA has been issued and its
+                    // LDS -> R2UR latency would sit between every two MMAs
                     if (dual) {
-#pragma unroll 2
+                        uint2 n0 = dl[e], n1 = dl[e + 1 < e1 ? e + 1 : e];
                         for (; e + 1 < e1; e += 2) {
-                            const uint2 o0 = dl[e], o1 = dl[e + 1];
+                            const uint2 o0 = n0, o1 = n1;
+                            if (e + 2 < e1) { n0 = dl[e + 2]; n1 = dl[e + 3 < e1 ? e + 3 : e + 2]; }
                             tc_mma_bf16(d_tmem, hi_c | (uint64_t)o0.x, hi_c | (uint64_t)(o0.y + tile_b), idesc, acc0);
                             tc_mma_bf16(d_tmem + nout, hi_c | (uint64_t)o1.x, hi_c | (uint64_t)(o1.y + tile_b), idesc, acc1);
                             acc0 = 1; acc1 = 1;
                         }
-                    }
-                    for (; e < e1; ++e) {
-                        const uint2 o = dl[e];
-                        tc_mma_bf16(d_tmem, hi_c | (uint64_t)o.x, hi_c | (uint64_t)(o.y + tile_b), idesc, acc0);
-                        acc0 = 1;
+                        if (e < e1) {                                      // odd count: the last descriptor is already in n0
+                            tc_mma_bf16(d_tmem, hi_c | (uint64_t)n0.x, hi_c | (uint64_t)(n0.y + tile_b), idesc, acc0);
+                            acc0 = 1; ++e;
+                        }
+                    } else if (e < e1) {
+                        uint2 n = dl[e];
+                        for (; e < e1; ++e) {
+                            const uint2 o = n;
+                            if (e + 1 < e1) n = dl[e + 1];
+                            tc_mma_bf16(d_tmem, hi_c | (uint64_t)o.x, hi_c | (uint64_t)(o.y + tile_b), idesc, acc0);
+                            acc0 = 1;
+                        }
                     }
                     tc_commit(smem_u32(empty + slot));               // frees the smem slot when the MMAs retire
                     if (++slot == slot0 + nsl) { slot = slot0; phase ^= 1; }
