@@ -476,8 +476,11 @@ template <int MODE> __device__ __forceinline__ uint64_t lerp2(uint64_t w0, uint6
 // along x / y whole warps / quarter-warps outside the grid skip the step (no LSU wavefronts).
 // ------------------------------------------------------------------------------------------------
 constexpr int GCK = GC + 1, GCN = GC * GC * GCK;                               // 5 x 5 x 6 corners per (tile, camera)
-constexpr int GS_SLOTS = 4, GS_THREADS = 32 * (4 + GS_SLOTS);                  // box slots = producer warps; 4 gather warps
-constexpr int GS_HDR = 1280, GS_META = GCN * 8;                                // header: corners (1200 B), then the int4 box
+#ifndef GS_SLOTS_V
+#define GS_SLOTS_V 4
+#endif
+constexpr int GS_PROD = 4, GS_SLOTS = GS_SLOTS_V, GS_THREADS = 32 * (4 + GS_PROD);  // 4 producer warps, 4 gather warps, GS_SLOTS box slots
+constexpr int GS_META = GCN * 8, GS_HDR = GS_META + 16;                        // header: corners (1200 B), then the int4 box
 constexpr int GS_CORNERS_PER_LANE = (GCN + 31) / 32;
 
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
@@ -539,7 +542,7 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
         int go[GS_CORNERS_PER_LANE];
         int go_tl = -1;
         const float2 *csrc = cab;
-        auto prefetch = [&](int n) {                                           // corners of item n -> its header (LDGSTS)
+        auto prefetch = [&](int n, int hidx) {                                 // corners of item n -> header hidx (LDGSTS)
             const int tl = n / ncam, c = n - tl * ncam;
             if (tl != go_tl) {
                 go_tl = tl;
@@ -550,21 +553,24 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
                 csrc = cab + (size_t)b * ncam * nc;
             }
             const float2 *src = csrc + (size_t)c * nc;
-            const uint32_t dst = smem_u32(hdrs + (n % (2 * GS_SLOTS)) * GS_HDR);
+            const uint32_t dst = smem_u32(hdrs + hidx * GS_HDR);
 #pragma unroll
             for (int r = 0; r < GS_CORNERS_PER_LANE; ++r)
                 if (lane + 32 * r < GCN) cp_async8(dst + (uint32_t)(lane + 32 * r) * 8u, src + go[r]);
             cp_async_commit();
         };
-        if (p < total) prefetch(p);
-        uint32_t ph = 0;
-        for (int n = p; n < total; n += GS_SLOTS) {
+        // item n lives in box slot n % GS_SLOTS and header n % (2 GS_SLOTS); producer p takes the items p, p + GS_PROD, ...
+        // (slot, wrap parity, header) advance by GS_PROD per item without a division
+        if (p < total) prefetch(p, p);
+        int slot = p, hidx = p; uint32_t ph = 0;                               // GS_PROD <= GS_SLOTS: the first items start in slot p, use 0
+        bool reuse = false;                                                    // the slot has had an earlier item
+        for (int n = p; n < total; n += GS_PROD) {
             cp_async_wait<0>();
             __syncwarp();                                                      // all lanes' copies visible to all lanes
             // pixel box bounding every index of the tile: each ATen lerp is a rounded convex combination, so the fine
             // coordinates stay inside the corners' range; (v / 2).int() is monotone, so the box is the integer
             // min / max of the corners' own pixels (REDUX instead of a float shuffle tree)
-            uint8_t *hd = hdrs + (n % (2 * GS_SLOTS)) * GS_HDR;
+            uint8_t *hd = hdrs + hidx * GS_HDR;
             int x0, x1, y0, y1;
             {
                 const float2 *cn = reinterpret_cast<const float2 *>(hd);
@@ -608,9 +614,9 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
             if (pitch * bh * G_PIX_BYTES > box_limit) pitch = bw | 1;
             if (pitch * bh * G_PIX_BYTES > box_limit) pitch = bw;
             if (pitch * bh * G_PIX_BYTES > box_limit || x0 < 0 || y0 < 0 || x1 >= hs || y1 >= hs) pitch = 0;
-            if (lane == 0) *reinterpret_cast<int4 *>(hd + GS_META) = make_int4(x0, y0, p * cap_bytes, pitch);
-            const uint32_t fb = smem_u32(full + p);
-            if (n >= GS_SLOTS) { mbar_wait_parked(smem_u32(empty + p), ph); ph ^= 1u; }   // item n - GS_SLOTS is done: slot + older header free
+            if (lane == 0) *reinterpret_cast<int4 *>(hd + GS_META) = make_int4(x0, y0, slot * cap_bytes, pitch);
+            const uint32_t fb = smem_u32(full + slot);
+            if (reuse) mbar_wait_parked(smem_u32(empty + slot), ph ^ 1u);      // item n - GS_SLOTS is done: slot + older header free
             __syncwarp();                                                      // every lane's corner copies + the box precede the arrive
             if (pitch == 0) {
                 if (lane == 0) mbar_arrive(fb);                                // box too large: gathered from global memory
@@ -620,13 +626,18 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
                 __syncwarp();
                 const int tl = n / ncam, c = n - tl * ncam;
                 const int b = ((int)blockIdx.x + tl * (int)gridDim.x) / tiles_fs;
-                uint8_t *box = gsm + (size_t)p * cap_bytes;
+                uint8_t *box = gsm + (size_t)slot * cap_bytes;
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(hm) + ((((size_t)b * ncam + c) * hs + y0) * hs + x0) * G_PIX_BYTES;
                 const int rowB = pitch * G_PIX_BYTES;
                 for (int r = lane; r < bh; r += 32)
                     bulk_load(smem_u32(box + (size_t)r * rowB), src + (size_t)r * hs * G_PIX_BYTES, row_bytes, fb);
             }
-            if (n + GS_SLOTS < total) prefetch(n + GS_SLOTS);                  // into the header item n - GS_SLOTS just released
+            // next item of this producer: slot / header advance by GS_PROD; its corners go into header (n + GS_PROD) % (2 GS_SLOTS),
+            // last used by item n + GS_PROD - 2 GS_SLOTS, which was released before item n - GS_SLOTS (waited for above)
+            slot += GS_PROD; hidx += GS_PROD;
+            if (slot >= GS_SLOTS) { slot -= GS_SLOTS; ph ^= 1u; reuse = true; }
+            if (hidx >= 2 * GS_SLOTS) hidx -= 2 * GS_SLOTS;
+            if (n + GS_PROD < total) prefetch(n + GS_PROD, hidx);
         }
         return;
     }
@@ -772,7 +783,12 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
 }
 
 
-constexpr int GS_CAP = 15360;                                                  // bytes per pixel-box slot of the streaming kernel
+#ifndef GS_CAP_V
+#define GS_CAP_V 15360
+#endif
+constexpr int GS_CAP = GS_CAP_V;                                               // bytes per pixel-box slot.  The boxes of an 8^3 tile average 96 pixels
+                                                                               // (4.6 KB, max 224 at the Example shape); six slots of 10 KB instead of four of
+                                                                               // 15 KB (GS_SLOTS_V=6, GS_CAP_V=10240) were measured SLOWER: 0.726 vs 0.690 ms (run 31)
 static std::atomic<int> g_box_limit{GS_CAP};                                   // boxes above this gather from global memory (test hook)
 int gather_set_box_bytes(int bytes)
 {
