@@ -149,6 +149,9 @@ int jhn_upload_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, c
  *                             bytes_pulled (optional, device u64) is incremented by the bytes read over the link. */
 int jhn_pull_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, const int32_t *boxes, int n_images, int hs,
                            int pixel_bytes, unsigned long long *bytes_pulled, jhn_stream_t stream);
+/*   jhn_debug_set_pull_config tuning hook: launch shape of the pull kernel — threads per CTA (32, 64, 96 or 128), number of
+ *                             CTAs, parts per image; an argument <= 0 leaves that value unchanged. */
+void jhn_debug_set_pull_config(int threads, int ctas, int split);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 2 — replaces V2VNet (jarvis/hybridnet/v2vnet.py:86-102) in eval mode.

@@ -54,6 +54,7 @@ SYMBOLS = {
     "jhn_profile_enable": (None, [c_int]),
     "jhn_profile_collect": (c_int, [c_char_p, c_int]),
     "jhn_debug_set_gather_box_bytes": (c_int, [c_int]),
+    "jhn_debug_set_pull_config": (None, [c_int, c_int, c_int]),
 }
 
 _lib = None

@@ -96,6 +96,7 @@ int crop_normalize_launch(const float *imgs, int B, int ncam, int H, int W, int 
 int heatmap_boxes_launch(const float *cam, const float *intr, const float *dist, const float *center3D, const int32_t *centerHM,
                          int B, int ncam, int hs, int G, float spacing, int32_t *boxes, cudaStream_t st);
 
+void pull_set_config(int threads, int ctas, int split);
 int pull_boxes_launch(const void *host_mapped, void *dev, const int32_t *boxes, int n_images, int hs, int pixel_bytes,
                       unsigned long long *bytes_out, cudaStream_t st);
 // ingest.cu (rows f4 / a11) and head2d.cu (row f2)

@@ -65,9 +65,17 @@ __device__ __forceinline__ void c3_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, 
         : "memory");
 }
 
+// Register cap of the 480-thread configuration (NOUT <= 48, EW = 3): 120 instead of the 128 that __launch_bounds__(480) lets
+// ptxas take.  15 warps x 120 registers leave 1024 registers free in every scheduler partition of the SM — what one warp of
+// the 32-register host-memory pull kernel (jhn_pull_heatmap_boxes) needs.  With 128 the pull CTAs and this kernel's CTAs keep
+// each other off an SM, and a forward that overlaps a transfer runs the 3x3x3 layers in two waves (tools/coreside_probe.py).
+// A thread bound cannot express 120 (544 threads = 5 warps per partition -> 96), hence __maxnreg__.
+#ifndef C3_MAXNREG_480
+#define C3_MAXNREG_480 120
+#endif
 // EW = epilogue warps per TMEM lane quadrant; each owns NOUT / EW output channels
 template <int NOUT, int EW>
-__global__ void __launch_bounds__(96 + 128 * EW, 1)
+__global__ void __maxnreg__(96 + 128 * EW == 480 ? C3_MAXNREG_480 : 168)
 tc_conv3_kernel(const C3Launch L)
 {
     constexpr int C3_THREADS = 96 + 128 * EW;

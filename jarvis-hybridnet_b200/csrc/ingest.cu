@@ -14,6 +14,7 @@
 //   pad_border_kernel         jarvis/hybridnet/model.py:65-66   heatmaps_padded = F.pad(heatmaps, [1,1,1,1])
 // All four are HBM-bound streaming kernels: 16-byte accesses, one pass.
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -117,13 +118,23 @@ pad_border_kernel(const float *__restrict__ in, int S, long long n_out, float *_
 // one such CTA fits next to the persistent convolution / gather CTAs (they leave 4096 registers and, with
 // JHN_SMEM_RESERVE, 3 KB of shared memory per SM free), so the transfer of chunk i+1 overlaps the kernels of chunk i
 // without ever keeping a compute CTA off an SM — a grid with one CTA per work item did exactly that.
-constexpr int PULL_THREADS = 128, PULL_SPLIT = 8, PULL_UNROLL = 2, PULL_CTAS = 48;
-__global__ void __launch_bounds__(PULL_THREADS, 16)
-pull_boxes_kernel(const uint4 *__restrict__ host, uint4 *__restrict__ dev, const int4 *__restrict__ boxes, int n_images, int hs,
-                  int units_per_pixel, unsigned long long *__restrict__ bytes_out)
+constexpr int PULL_MAX_THREADS = 128, PULL_UNROLL = 2;
+// Launch shape, settable at run time (jhn_debug_set_pull_config): threads per CTA (32..128), CTAs, parts per image.
+static std::atomic<int> g_pull_threads{128}, g_pull_ctas{48}, g_pull_split{8};
+void pull_set_config(int threads, int ctas, int split)
 {
-    for (int w = blockIdx.x; w < n_images * PULL_SPLIT; w += gridDim.x) {
-        const int img = w / PULL_SPLIT, part = w - img * PULL_SPLIT;
+    if (threads >= 32 && threads <= PULL_MAX_THREADS && threads % 32 == 0) g_pull_threads.store(threads, std::memory_order_relaxed);
+    if (ctas >= 1) g_pull_ctas.store(ctas, std::memory_order_relaxed);
+    if (split >= 1 && split <= 64) g_pull_split.store(split, std::memory_order_relaxed);
+}
+
+__global__ void __launch_bounds__(PULL_MAX_THREADS, 16)
+pull_boxes_kernel(const uint4 *__restrict__ host, uint4 *__restrict__ dev, const int4 *__restrict__ boxes, int n_images, int hs,
+                  int units_per_pixel, int split, unsigned long long *__restrict__ bytes_out)
+{
+    const int nthr = blockDim.x;
+    for (int w = blockIdx.x; w < n_images * split; w += gridDim.x) {
+        const int img = w / split, part = w - img * split;
         const int4 bx = __ldg(boxes + img);                           // {x0, y0, -x1, -y1}
         const int x0 = bx.x, y0 = bx.y, bw = -bx.z - bx.x + 1, bh = -bx.w - bx.y + 1;
         if (x0 < 0 || y0 < 0 || bw < 1 || bh < 1 || x0 + bw > hs || y0 + bh > hs) continue;  // no box: nothing the gather could read
@@ -132,8 +143,8 @@ pull_boxes_kernel(const uint4 *__restrict__ host, uint4 *__restrict__ dev, const
         const size_t base = (size_t)img * hs * pitch_units + (size_t)y0 * pitch_units + (size_t)x0 * units_per_pixel;
         const uint4 *src = host + base;
         uint4 *dst = dev + base;
-        constexpr int stride = PULL_THREADS * PULL_SPLIT;
-        for (int u0 = part * PULL_THREADS + threadIdx.x; u0 < total; u0 += stride * PULL_UNROLL) {
+        const int stride = nthr * split;
+        for (int u0 = part * nthr + threadIdx.x; u0 < total; u0 += stride * PULL_UNROLL) {
             uint4 v[PULL_UNROLL];
             int off[PULL_UNROLL];
 #pragma unroll
@@ -154,10 +165,11 @@ pull_boxes_kernel(const uint4 *__restrict__ host, uint4 *__restrict__ dev, const
 int pull_boxes_launch(const void *host_mapped, void *dev, const int32_t *boxes, int n_images, int hs, int pixel_bytes,
                       unsigned long long *bytes_out, cudaStream_t st)
 {
+    const int threads = g_pull_threads.load(std::memory_order_relaxed), split = g_pull_split.load(std::memory_order_relaxed);
+    const int ctas = std::min(g_pull_ctas.load(std::memory_order_relaxed), n_images * split);
     JHN_LAUNCH("pull_boxes_kernel", st,
-               pull_boxes_kernel<<<std::min(PULL_CTAS, n_images * PULL_SPLIT), PULL_THREADS, 0, st>>>((const uint4 *)host_mapped, (uint4 *)dev,
-                                                                                                       (const int4 *)boxes, n_images, hs,
-                                                                                                       pixel_bytes / 16, bytes_out));
+               pull_boxes_kernel<<<ctas, threads, 0, st>>>((const uint4 *)host_mapped, (uint4 *)dev, (const int4 *)boxes, n_images, hs,
+                                                           pixel_bytes / 16, split, bytes_out));
     return JHN_OK;
 }
 

@@ -213,11 +213,11 @@ class HybridNet3D(nn.Module):
         actually crossed the link.  == forward_host_async(...).result(); see there."""
         return self.forward_host_async(host_inputs, chunk, roi_upload).result()
 
-    def forward_host_async(self, host_inputs, chunk=8, roi_upload="dma"):
+    def forward_host_async(self, host_inputs, chunk=8, roi_upload="dma", slots=2):
         """Enqueue one end-to-end step and return a handle whose .result() waits for it: (pinned [B,K,4], h2d_bytes, d2h_bytes).
 
         The batch is cut into chunks of `chunk` frame sets: a copy stream uploads chunk i+1 while the compute stream runs
-        chunk i.  Two sets of device buffers alternate between calls, so a caller that submits step n+1 before it collects
+        chunk i.  `slots` sets of device buffers alternate between calls, so a caller that submits step n+1 before it collects
         step n keeps the link busy while step n computes (each step still uploads its own inputs and downloads its own
         result; a step costs max(PCIe time, kernel time) in steady state).
 
@@ -226,17 +226,18 @@ class HybridNet3D(nn.Module):
         them.  roi_upload "dma" (default): strided copy-engine transfers, all boxes of a chunk in one
         cudaMemcpy3DBatchAsync (jhn_upload_heatmap_boxes; ~36 GB/s on 5 KB rows, against 55 GB/s for a contiguous copy of
         1.8x the bytes); "pull": a small kernel reads the boxes out of the mapped host tensor (jhn_pull_heatmap_boxes,
-        47 GB/s alone, but its CTAs cannot share an SM with the 14-warp convolution kernel, so it overlaps compute badly);
-        None: whole tensors."""
+        45 GB/s; every compute kernel runs ~20 % slower while it is active); "hybrid:f": both at once — the copy engine takes
+        the first 1 - f of every chunk's images, the pull kernel the rest (f = 0.6 with chunk = B is the fastest measured:
+        4.28 ms per 32 frame sets against 5.1 - 5.4 for "dma", profiles/r02_e2e_hybrid_upload.txt); None: whole tensors."""
         dev = torch.device("cuda", torch.cuda.current_device())
         lib = _lib.load()
         B = host_inputs[0].shape[0]
         chunk = max(1, min(chunk, B))
-        key = tuple((tuple(t.shape), t.dtype) for t in host_inputs)
+        key = tuple((tuple(t.shape), t.dtype) for t in host_inputs) + (int(slots),)
         if self._host is None or self._host["key"] != key:
             ncam = host_inputs[0].shape[1]
-            slots = []
-            for _ in range(2):
+            n_slots, slots = max(2, int(slots)), []
+            for _ in range(n_slots):
                 dbuf = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host_inputs]
                 if host_inputs[0].dtype in (torch.float16, torch.bfloat16):
                     dbuf[0].zero_()                          # pixels outside the boxes are never read; keep them finite anyway
@@ -249,17 +250,21 @@ class HybridNet3D(nn.Module):
             self._host = dict(key=key, slots=slots, n=0, copy=torch.cuda.Stream(device=dev, priority=-1),
                               aux=torch.cuda.Stream(device=dev, priority=-1))
         H = self._host
-        S = H["slots"][H["n"] % 2]
+        S = H["slots"][H["n"] % len(H["slots"])]
         H["n"] += 1
         if S["busy"] is not None:
-            S["busy"].result()                           # the step that used this slot two calls ago must have been collected
+            S["busy"].result()                           # the step that last used this slot must have been collected
         dbuf, res, hres, boxes, hboxes, pulled, hpulled = (S[k] for k in ("dbuf", "res", "hres", "boxes", "hboxes", "pulled", "hpulled"))
         copy_stream, aux = H["copy"], H["aux"]
         main = torch.cuda.current_stream()
         hm_h = host_inputs[0]
         roi = roi_upload if (roi_upload and hm_h.dtype in (torch.float16, torch.bfloat16) and hm_h.is_pinned()) else None
-        if roi not in (None, "pull", "dma"):
-            raise ValueError("roi_upload must be 'pull', 'dma' or None")
+        pull_frac = 0.0
+        if isinstance(roi, str) and roi.startswith("hybrid"):          # "hybrid:0.25" = a quarter of every chunk's images by the pull kernel
+            pull_frac = float(roi.split(":")[1]) if ":" in roi else 0.25
+            roi = "hybrid"
+        if roi not in (None, "pull", "dma", "hybrid"):
+            raise ValueError("roi_upload must be 'pull', 'dma', 'hybrid[:fraction]' or None")
         if S["done"] is not None:
             copy_stream.wait_event(S["done"])            # the kernels of the slot's previous step are done with its device buffers
             aux.wait_event(S["done"])
@@ -285,31 +290,49 @@ class HybridNet3D(nn.Module):
                     pulled.zero_()
                 small = torch.cuda.Event()
                 small.record(aux)
-            if roi == "dma":
+            if roi in ("dma", "hybrid"):
                 small.synchronize()                      # 1.5 KB back: the host needs the boxes to describe the strided copies
             copy_stream.wait_event(small)
             main.wait_event(small)
-            with torch.cuda.stream(copy_stream):
-                sp = ctypes.c_void_p(copy_stream.cuda_stream)
-                copied = _lib.c_size_t()
-                for lo in range(0, B, chunk):
-                    n = min(chunk, B - lo)
-                    src = ctypes.c_void_p(hm_h.data_ptr() + lo * ncam * img)
-                    dst = ctypes.c_void_p(dbuf[0].data_ptr() + lo * ncam * img)
-                    if roi == "dma":
-                        _lib.check(lib.jhn_upload_heatmap_boxes(src, dst, ctypes.c_void_p(hboxes.data_ptr() + lo * ncam * 16), n * ncam,
-                                                                hs, pix, sp, ctypes.byref(copied)))
-                        h2d += copied.value
-                    else:
-                        _lib.check(lib.jhn_pull_heatmap_boxes(src, dst, ctypes.c_void_p(boxes.data_ptr() + lo * ncam * 16), n * ncam,
-                                                              hs, pix, _lib.dptr(pulled), sp))
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    events.append(ev)
-                if roi == "pull":
+            ps = copy_stream                             # stream of the pull kernel
+            if roi == "hybrid":
+                # The copy engine is bound by rows per second (~36 GB/s on these 5 KB rows), the link is not (55 GB/s): the pull
+                # kernel moves the LAST pull_frac of every chunk's images over the link while the copy engine walks the rest.
+                if "pull" not in H:
+                    H["pull"] = torch.cuda.Stream(device=dev)
+                ps = H["pull"]
+                ps.wait_event(small)
+                if S["done"] is not None:
+                    ps.wait_event(S["done"])
+            sp, spull = ctypes.c_void_p(copy_stream.cuda_stream), ctypes.c_void_p(ps.cuda_stream)
+            copied = _lib.c_size_t()
+            for lo in range(0, B, chunk):
+                n_img = min(chunk, B - lo) * ncam
+                n_pull = {"dma": 0, "pull": n_img}.get(roi, min(n_img, max(0, int(round(pull_frac * n_img)))))
+                n_dma, i0 = n_img - n_pull, lo * ncam
+                evs = []
+                if n_dma:
+                    _lib.check(lib.jhn_upload_heatmap_boxes(ctypes.c_void_p(hm_h.data_ptr() + i0 * img), ctypes.c_void_p(dbuf[0].data_ptr() + i0 * img),
+                                                            ctypes.c_void_p(hboxes.data_ptr() + i0 * 16), n_dma, hs, pix, sp, ctypes.byref(copied)))
+                    h2d += copied.value
+                    evs.append(torch.cuda.Event())
+                    evs[-1].record(copy_stream)
+                if n_pull:
+                    j0 = i0 + n_dma
+                    _lib.check(lib.jhn_pull_heatmap_boxes(ctypes.c_void_p(hm_h.data_ptr() + j0 * img), ctypes.c_void_p(dbuf[0].data_ptr() + j0 * img),
+                                                          ctypes.c_void_p(boxes.data_ptr() + j0 * 16), n_pull, hs, pix,
+                                                          _lib.dptr(pulled) if roi == "pull" else None, spull))
+                    if roi == "hybrid":                  # the host has the boxes: count the pulled bytes here
+                        b4 = hboxes.view(-1, 4)[j0:j0 + n_pull].to(torch.int64)
+                        h2d += int(((1 - b4[:, 2] - b4[:, 0]).clamp_(min=0) * (1 - b4[:, 3] - b4[:, 1]).clamp_(min=0)).sum()) * pix
+                    evs.append(torch.cuda.Event())
+                    evs[-1].record(ps)
+                events.append(evs)
+            if roi == "pull":
+                with torch.cuda.stream(copy_stream):
                     hpulled.copy_(pulled, non_blocking=True)
-                    done_copy = torch.cuda.Event()
-                    done_copy.record(copy_stream)
+                done_copy = torch.cuda.Event()
+                done_copy.record(copy_stream)
         else:
             with torch.cuda.stream(copy_stream):
                 for lo in range(0, B, chunk):
@@ -317,10 +340,11 @@ class HybridNet3D(nn.Module):
                         d[lo:lo + chunk].copy_(h[lo:lo + chunk], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
-                    events.append(ev)
+                    events.append([ev])
             h2d = sum(t.numel() * t.element_size() for t in host_inputs)
         for i, lo in enumerate(range(0, B, chunk)):
-            main.wait_event(events[i])
+            for ev in events[i]:
+                main.wait_event(ev)
             pts, conf, _ = self.forward(*[d[lo:lo + chunk] for d in dbuf])
             res[lo:lo + chunk, :, :3] = pts
             res[lo:lo + chunk, :, 3] = conf

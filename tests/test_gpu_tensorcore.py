@@ -119,8 +119,14 @@ def test_forward_host_uploads_only_the_pixel_boxes():
     assert h2d < full and h2d > sum(t.numel() * t.element_size() for t in host[1:])
     res, h2d_pull, _ = net.forward_host(host, chunk=2, roi_upload="pull")  # boxes read out of mapped host memory by a kernel
     assert torch.equal(res, want) and h2d_pull == h2d
+    # both at once: the copy engine takes the first images of every chunk, the pull kernel the rest; other launch shapes of the pull kernel
+    for mode, shape in (("hybrid:0.6", (128, 48, 8)), ("hybrid:0.25", (32, 7, 3)), ("hybrid:1.0", (64, 200, 1)), ("hybrid:0", (128, 48, 8))):
+        _lib.load().jhn_debug_set_pull_config(*shape)
+        res, h2d_h, _ = net.forward_host(host, chunk=2, roi_upload=mode)
+        assert torch.equal(res, want) and h2d_h == h2d, mode
+    _lib.load().jhn_debug_set_pull_config(128, 48, 8)
     # poison everything on the device, upload the boxes again: the gather must not see the poison
-    for mode in ("dma", "pull"):
+    for mode in ("dma", "pull", "hybrid:0.5"):
         for slot in net._host["slots"]:
             slot["dbuf"][0].view(torch.int16).fill_(0x7e00)          # fp16 NaN
         res, h2d2, _ = net.forward_host(host, chunk=2, roi_upload=mode)
@@ -134,7 +140,7 @@ def test_forward_host_uploads_only_the_pixel_boxes():
     assert torch.allclose(rb.flip(0), want, rtol=0, atol=5e-3)      # frame sets in another batch position: fp32 re-association only
     # the boxes bound the reference's indices (the fp32 path dumps them: repro_layer.py:82-83)
     from jarvis_hybridnet_b200 import ReprojectionLayer
-    boxes = net._host["slots"][1]["hboxes"].numpy()                  # pinned copy of jhn_heatmap_boxes' output (slot of step `a`)
+    boxes = a._slot["hboxes"].numpy()                                # pinned copy of jhn_heatmap_boxes' output (slot of step `a`)
     devt = [t.to(DEV) for t in host]
     from test_host import cfg_of
     layer = ReprojectionLayer(cfg_of(sh), sh.ncam, precision="fp32")
