@@ -149,6 +149,20 @@ int jhn_upload_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, c
  *                             bytes_pulled (optional, device u64) is incremented by the bytes read over the link. */
 int jhn_pull_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, const int32_t *boxes, int n_images, int hs,
                            int pixel_bytes, unsigned long long *bytes_pulled, jhn_stream_t stream);
+/*   jhn_heatmap_spans         jhn_heatmap_boxes plus, per (frame set, camera, pixel row), the column range the gather can touch:
+ *                             spans = int32 [B][ncam][hs][2] holding {lo, -hi} (rows no voxel maps to have lo > hi).  The spans
+ *                             hold ~78 % of the boxes' pixels (the voxel cube projects to a hexagon).  scratch: device,
+ *                             B * ncam * (G/2)^3 * 8 bytes (the coarse grid's projections).
+ *   jhn_pull_heatmap_spans    jhn_pull_heatmap_boxes over those row spans (device tensor `spans`). */
+int jhn_heatmap_spans(const float *cameraMatrices, const float *intrinsicMatrices, const float *distortionCoefficients,
+                      const float *center3D, const int32_t *centerHM, int B, int ncam, int hs, int G, float spacing,
+                      void *scratch, size_t scratch_bytes, int32_t *boxes, int32_t *spans, jhn_stream_t stream);
+int jhn_pull_heatmap_spans(const void *host_heatmaps, void *device_heatmaps, const int32_t *spans, int n_images, int hs,
+                           int pixel_bytes, unsigned long long *bytes_pulled, jhn_stream_t stream);
+/*   jhn_pull_small            n <= 8 small pinned host tensors (calibration, centres) copied to the device by one kernel that
+ *                             reads mapped host memory: unlike cudaMemcpyAsync they do not queue on the host->device copy
+ *                             engine behind a large transfer issued earlier on another stream.  bytes[k] % 4 == 0. */
+int jhn_pull_small(int n, const void *const *host_tensors, void *const *device_tensors, const size_t *bytes, jhn_stream_t stream);
 /*   jhn_debug_set_pull_config tuning hook: launch shape of the pull kernel — threads per CTA (32, 64, 96 or 128), number of
  *                             CTAs, parts per image; an argument <= 0 leaves that value unchanged. */
 void jhn_debug_set_pull_config(int threads, int ctas, int split);

@@ -55,6 +55,9 @@ SYMBOLS = {
     "jhn_profile_collect": (c_int, [c_char_p, c_int]),
     "jhn_debug_set_gather_box_bytes": (c_int, [c_int]),
     "jhn_debug_set_pull_config": (None, [c_int, c_int, c_int]),
+    "jhn_pull_small": (c_int, [c_int, _P, _P, _P, _P]),
+    "jhn_heatmap_spans": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, c_size_t, _P, _P, _P]),
+    "jhn_pull_heatmap_spans": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
 }
 
 _lib = None

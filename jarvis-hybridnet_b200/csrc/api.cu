@@ -402,6 +402,21 @@ int jhn_heatmap_boxes(const float *cameraMatrices, const float *intrinsicMatrice
                                 boxes, (cudaStream_t)stream);
 }
 
+int jhn_heatmap_spans(const float *cameraMatrices, const float *intrinsicMatrices, const float *distortionCoefficients,
+                      const float *center3D, const int32_t *centerHM, int B, int ncam, int hs, int G, float spacing,
+                      void *scratch, size_t scratch_bytes, int32_t *boxes, int32_t *spans, jhn_stream_t stream)
+{
+    if (!cameraMatrices || !intrinsicMatrices || !distortionCoefficients || !center3D || !centerHM || !boxes || !spans || !scratch)
+        return fail(JHN_ERR_ARG, "jhn_heatmap_spans: null pointer argument");
+    if (B < 1 || B > 65535 || ncam < 1 || ncam > 64) return fail(JHN_ERR_SHAPE, "need 1<=B<=65535, 1<=ncam<=64 (got B=%d ncam=%d)", B, ncam);
+    if (hs < 4 || G < 2 || (G & 1)) return fail(JHN_ERR_SHAPE, "need hs>=4 and an even grid side (got hs=%d G=%d)", hs, G);
+    const size_t h = (size_t)G / 2, need = (size_t)B * ncam * h * h * h * sizeof(float2);
+    if (scratch_bytes < need) return fail(JHN_ERR_WORKSPACE, "jhn_heatmap_spans scratch: need %zu bytes, got %zu", need, scratch_bytes);
+    if ((uintptr_t)scratch & 7) return fail(JHN_ERR_WORKSPACE, "jhn_heatmap_spans scratch must be 8-byte aligned");
+    return heatmap_spans_launch(cameraMatrices, intrinsicMatrices, distortionCoefficients, center3D, centerHM, B, ncam, hs, G, spacing,
+                                scratch, boxes, spans, (cudaStream_t)stream);
+}
+
 int jhn_upload_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, const int32_t *boxes_host, int n_images, int hs,
                              int pixel_bytes, jhn_stream_t stream, size_t *bytes_copied)
 {
@@ -499,11 +514,51 @@ int jhn_pull_heatmap_boxes(const void *host_heatmaps, void *device_heatmaps, con
         return fail(JHN_ERR_SHAPE, "need 1<=n_images<=65535, hs>=1, pixel_bytes a multiple of 16 (got %d, %d, %d)", n_images, hs, pixel_bytes);
     if (((uintptr_t)host_heatmaps | (uintptr_t)device_heatmaps) & 15) return fail(JHN_ERR_ARG, "jhn_pull_heatmap_boxes: tensors must be 16-byte aligned");
     void *mapped = nullptr;
-    if (cudaHostGetDevicePointer(&mapped, const_cast<void *>(host_heatmaps), 0) != cudaSuccess || !mapped) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host_heatmaps) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+        mapped = const_cast<void *>(host_heatmaps);           // a device tensor as the source: a box-only device-to-device copy
+    } else if (cudaHostGetDevicePointer(&mapped, const_cast<void *>(host_heatmaps), 0) != cudaSuccess || !mapped) {
         cudaGetLastError();
         return fail(JHN_ERR_ARG, "jhn_pull_heatmap_boxes: host_heatmaps is not pinned, device-mapped host memory (cudaHostAlloc / cudaHostRegister)");
     }
     return pull_boxes_launch(mapped, device_heatmaps, boxes, n_images, hs, pixel_bytes, bytes_pulled, (cudaStream_t)stream);
+}
+
+int jhn_pull_heatmap_spans(const void *host_heatmaps, void *device_heatmaps, const int32_t *spans, int n_images, int hs,
+                           int pixel_bytes, unsigned long long *bytes_pulled, jhn_stream_t stream)
+{
+    if (!host_heatmaps || !device_heatmaps || !spans) return fail(JHN_ERR_ARG, "jhn_pull_heatmap_spans: null pointer argument");
+    if (n_images < 1 || n_images > 65535 || hs < 1 || pixel_bytes < 16 || (pixel_bytes % 16) != 0)
+        return fail(JHN_ERR_SHAPE, "need 1<=n_images<=65535, hs>=1, pixel_bytes a multiple of 16 (got %d, %d, %d)", n_images, hs, pixel_bytes);
+    if (((uintptr_t)host_heatmaps | (uintptr_t)device_heatmaps) & 15) return fail(JHN_ERR_ARG, "jhn_pull_heatmap_spans: tensors must be 16-byte aligned");
+    void *mapped = nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host_heatmaps) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+        mapped = const_cast<void *>(host_heatmaps);
+    } else if (cudaHostGetDevicePointer(&mapped, const_cast<void *>(host_heatmaps), 0) != cudaSuccess || !mapped) {
+        cudaGetLastError();
+        return fail(JHN_ERR_ARG, "jhn_pull_heatmap_spans: host_heatmaps is not pinned, device-mapped host memory (cudaHostAlloc / cudaHostRegister)");
+    }
+    return pull_spans_launch(mapped, device_heatmaps, spans, n_images, hs, pixel_bytes, bytes_pulled, (cudaStream_t)stream);
+}
+
+int jhn_pull_small(int n, const void *const *host_tensors, void *const *device_tensors, const size_t *bytes, jhn_stream_t stream)
+{
+    if (n < 1 || n > 8) return fail(JHN_ERR_ARG, "jhn_pull_small: 1 to 8 tensors per call (got %d)", n);
+    if (!host_tensors || !device_tensors || !bytes) return fail(JHN_ERR_ARG, "jhn_pull_small: null pointer argument");
+    const void *mapped[8];
+    for (int k = 0; k < n; ++k) {
+        if (!host_tensors[k] || !device_tensors[k]) return fail(JHN_ERR_ARG, "jhn_pull_small: tensor %d is null", k);
+        if ((bytes[k] & 3) || bytes[k] > (64u << 20) || (((uintptr_t)host_tensors[k] | (uintptr_t)device_tensors[k]) & 3))
+            return fail(JHN_ERR_ARG, "jhn_pull_small: tensor %d must be 4-byte aligned, a multiple of 4 bytes and <= 64 MB (got %zu bytes)", k, bytes[k]);
+        void *m = nullptr;
+        if (cudaHostGetDevicePointer(&m, const_cast<void *>(host_tensors[k]), 0) != cudaSuccess || !m) {
+            cudaGetLastError();
+            return fail(JHN_ERR_ARG, "jhn_pull_small: tensor %d is not pinned, device-mapped host memory (cudaHostAlloc / cudaHostRegister)", k);
+        }
+        mapped[k] = m;
+    }
+    return pull_segments_launch(n, mapped, device_tensors, bytes, (cudaStream_t)stream);
 }
 
 int jhn_ingest_frames(const uint8_t *frames, int N, int H, int W, float *imgs, jhn_stream_t stream)

@@ -97,6 +97,11 @@ int heatmap_boxes_launch(const float *cam, const float *intr, const float *dist,
                          int B, int ncam, int hs, int G, float spacing, int32_t *boxes, cudaStream_t st);
 
 void pull_set_config(int threads, int ctas, int split);
+int pull_spans_launch(const void *host_mapped, void *dev, const int32_t *spans, int n_images, int hs, int pixel_bytes,
+                      unsigned long long *bytes_out, cudaStream_t st);
+int heatmap_spans_launch(const float *cam, const float *intr, const float *dist, const float *center3D, const int32_t *centerHM,
+                         int B, int ncam, int hs, int G, float spacing, void *scratch, int32_t *boxes, int32_t *spans, cudaStream_t st);
+int pull_segments_launch(int n, const void *const *src_mapped, void *const *dst, const size_t *bytes, cudaStream_t st);
 int pull_boxes_launch(const void *host_mapped, void *dev, const int32_t *boxes, int n_images, int hs, int pixel_bytes,
                       unsigned long long *bytes_out, cudaStream_t st);
 // ingest.cu (rows f4 / a11) and head2d.cu (row f2)

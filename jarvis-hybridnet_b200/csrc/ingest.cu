@@ -118,6 +118,8 @@ pad_border_kernel(const float *__restrict__ in, int S, long long n_out, float *_
 // one such CTA fits next to the persistent convolution / gather CTAs (they leave 4096 registers and, with
 // JHN_SMEM_RESERVE, 3 KB of shared memory per SM free), so the transfer of chunk i+1 overlaps the kernels of chunk i
 // without ever keeping a compute CTA off an SM — a grid with one CTA per work item did exactly that.
+// (A row-granular variant — a warp per box row, no division per unit, ~5 instead of ~40 instructions per 16 bytes — slowed the
+// co-resident convolution CTAs just as much and made the hybrid upload slower, 4.7 vs 4.2 ms per step: run 48.)
 constexpr int PULL_MAX_THREADS = 128, PULL_UNROLL = 2;
 // Launch shape, settable at run time (jhn_debug_set_pull_config): threads per CTA (32..128), CTAs, parts per image.
 static std::atomic<int> g_pull_threads{128}, g_pull_ctas{48}, g_pull_split{8};
@@ -162,14 +164,174 @@ pull_boxes_kernel(const uint4 *__restrict__ host, uint4 *__restrict__ dev, const
     }
 }
 
+// An SM's shared-memory / L1 split is reconfigured only while the SM is idle.  A kernel without shared memory prefers the
+// smallest carve-out, so a pull CTA sitting alone on an SM pins that configuration — and the next persistent convolution CTA,
+// which needs nearly all of the SM's shared memory, must wait until the pull CTA has left: every persistent kernel of the
+// forward then runs in two waves (tools/coreside_probe.py with a sleeping dummy kernel: forward 2.98 -> 4.8 ms next to 48
+// idle CTAs, 3.06 ms once the dummy prefers the largest carve-out; profiles/r02_e2e_hybrid_upload.txt, runs 49 - 51).
+// The transfer kernels therefore ask for the LARGEST carve-out although they use no shared memory.
+template <typename F>
+static int prefer_max_carveout(F kern)
+{
+    static std::atomic<unsigned long long> configured{0ull};          // one bit per device
+    int dev = 0;
+    JHN_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        JHN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    return JHN_OK;
+}
+
 int pull_boxes_launch(const void *host_mapped, void *dev, const int32_t *boxes, int n_images, int hs, int pixel_bytes,
                       unsigned long long *bytes_out, cudaStream_t st)
 {
+    JHN_TRY(prefer_max_carveout(pull_boxes_kernel));
     const int threads = g_pull_threads.load(std::memory_order_relaxed), split = g_pull_split.load(std::memory_order_relaxed);
     const int ctas = std::min(g_pull_ctas.load(std::memory_order_relaxed), n_images * split);
     JHN_LAUNCH("pull_boxes_kernel", st,
                pull_boxes_kernel<<<ctas, threads, 0, st>>>((const uint4 *)host_mapped, (uint4 *)dev, (const int4 *)boxes, n_images, hs,
                                                            pixel_bytes / 16, split, bytes_out));
+    return JHN_OK;
+}
+
+// The same transfer restricted to each pixel row's column span (jhn_heatmap_spans): a warp per row, work item = (image, part).
+__global__ void __launch_bounds__(PULL_MAX_THREADS, 16)
+pull_spans_kernel(const uint4 *__restrict__ host, uint4 *__restrict__ dev, const int2 *__restrict__ spans, int n_images, int hs,
+                  int units_per_pixel, int split, unsigned long long *__restrict__ bytes_out)
+{
+    const int nw = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ptrdiff_t to_dev = reinterpret_cast<const char *>(dev) - reinterpret_cast<const char *>(host);
+    const int pitch_units = hs * units_per_pixel;
+    unsigned long long moved = 0;
+    for (int w = blockIdx.x; w < n_images * split; w += gridDim.x) {
+        const int img = w / split, part = w - img * split;
+        for (int y = part * nw + wid; y < hs; y += split * nw) {
+            const int2 sp = __ldg(spans + (size_t)img * hs + y);      // {lo, -hi}
+            const int lo = sp.x, hi = -sp.y;
+            if (lo < 0 || hi >= hs || hi < lo) continue;              // no voxel maps to this row
+            const int units = (hi - lo + 1) * units_per_pixel;
+            const uint4 *src = host + ((size_t)img * hs + y) * pitch_units + (size_t)lo * units_per_pixel + lane;
+            for (int left = units - lane; left > 0; left -= 32 * PULL_UNROLL, src += 32 * PULL_UNROLL) {
+                uint4 v[PULL_UNROLL];
+#pragma unroll
+                for (int k = 0; k < PULL_UNROLL; ++k)
+                    if (32 * k < left) v[k] = __ldcs(src + 32 * k);
+                uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(const_cast<uint4 *>(src)) + to_dev);
+#pragma unroll
+                for (int k = 0; k < PULL_UNROLL; ++k)
+                    if (32 * k < left) dst[32 * k] = v[k];
+            }
+            moved += (unsigned long long)units * 16ull;
+        }
+    }
+    if (bytes_out && lane == 0 && moved) atomicAdd(bytes_out, moved);
+}
+
+// Maps of up to PULL_FLAT_HS rows: the spans of an image are flattened into one run of 16-byte units (prefix sums of the row
+// widths in 1.5 KB of shared memory — what a convolution CTA leaves free on its SM) and the threads stride through that run
+// exactly as pull_boxes_kernel strides through a box: two independent loads in flight per thread, no partly filled warps at
+// row ends.  (The warp-per-row kernel above loses ~25 % of the link to those: 4.45 vs 4.11 ms per step, run 53.)
+constexpr int PULL_FLAT_HS = 256;
+__global__ void __launch_bounds__(PULL_MAX_THREADS, 16)
+pull_spans_flat_kernel(const uint4 *__restrict__ host, uint4 *__restrict__ dev, const int2 *__restrict__ spans, int n_images, int hs,
+                       int units_per_pixel, int split, unsigned long long *__restrict__ bytes_out)
+{
+    __shared__ int pre[PULL_FLAT_HS + 1];                             // pixels in the rows before row y
+    __shared__ short lo_s[PULL_FLAT_HS];
+    const int nthr = blockDim.x, lane = threadIdx.x & 31;
+    const int per = (hs + 31) / 32;                                   // rows per lane of the scanning warp
+    for (int w = blockIdx.x; w < n_images * split; w += gridDim.x) {
+        const int img = w / split, part = w - img * split;
+        __syncthreads();                                              // the previous item's tables are no longer read
+        for (int y = threadIdx.x; y < hs; y += nthr) {
+            const int2 sp = __ldg(spans + (size_t)img * hs + y);      // {lo, -hi}
+            const int lo = sp.x, hi = -sp.y;
+            const bool ok = lo >= 0 && hi < hs && hi >= lo;
+            pre[y + 1] = ok ? hi - lo + 1 : 0;
+            lo_s[y] = (short)(ok ? lo : 0);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {                                       // exclusive scan: a chunk of rows per lane, then the lanes
+            int sum = 0;
+            for (int i = 0; i < per; ++i) { const int y = lane * per + i; if (y < hs) sum += pre[y + 1]; }
+            int incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+            int run = incl - sum;
+            for (int i = 0; i < per; ++i) { const int y = lane * per + i; if (y < hs) { const int wd = pre[y + 1]; pre[y + 1] = run + wd; run += wd; } }
+            if (lane == 0) pre[0] = 0;
+        }
+        __syncthreads();
+        const int total = pre[hs] * units_per_pixel;
+        const size_t base = (size_t)img * hs * hs * units_per_pixel;
+        const uint4 *src = host + base;
+        uint4 *dst = dev + base;
+        const int stride = nthr * split;
+        for (int u0 = part * nthr + threadIdx.x; u0 < total; u0 += stride * PULL_UNROLL) {
+            uint4 v[PULL_UNROLL];
+            int off[PULL_UNROLL];
+#pragma unroll
+            for (int k = 0; k < PULL_UNROLL; ++k) {
+                const int u = u0 + k * stride;
+                const int px = u / units_per_pixel;
+                int a = 0, b = hs;                                    // last row with pre[row] <= px
+                while (b - a > 1) { const int m = (a + b) >> 1; if (pre[m] <= px) a = m; else b = m; }
+                off[k] = (a * hs + lo_s[a] - pre[a]) * units_per_pixel + u;
+                if (u < total) v[k] = __ldcs(src + off[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < PULL_UNROLL; ++k)
+                if (u0 + k * stride < total) dst[off[k]] = v[k];
+        }
+        if (bytes_out && part == 0 && threadIdx.x == 0) atomicAdd(bytes_out, (unsigned long long)total * 16ull);
+    }
+}
+
+int pull_spans_launch(const void *host_mapped, void *dev, const int32_t *spans, int n_images, int hs, int pixel_bytes,
+                      unsigned long long *bytes_out, cudaStream_t st)
+{
+    JHN_TRY(prefer_max_carveout(pull_spans_kernel));
+    const int threads = g_pull_threads.load(std::memory_order_relaxed), split = g_pull_split.load(std::memory_order_relaxed);
+    const int ctas = std::min(g_pull_ctas.load(std::memory_order_relaxed), n_images * split);
+    if (hs <= PULL_FLAT_HS) {
+        JHN_TRY(prefer_max_carveout(pull_spans_flat_kernel));
+        JHN_LAUNCH("pull_spans_flat_kernel", st,
+                   pull_spans_flat_kernel<<<ctas, threads, 0, st>>>((const uint4 *)host_mapped, (uint4 *)dev, (const int2 *)spans, n_images, hs,
+                                                                    pixel_bytes / 16, split, bytes_out));
+        return JHN_OK;
+    }
+    JHN_LAUNCH("pull_spans_kernel", st,
+               pull_spans_kernel<<<ctas, threads, 0, st>>>((const uint4 *)host_mapped, (uint4 *)dev, (const int2 *)spans, n_images, hs,
+                                                           pixel_bytes / 16, split, bytes_out));
+    return JHN_OK;
+}
+
+// A handful of small host tensors (calibration, centres: ~1.4 KB per frame set) read out of mapped host memory by ONE small
+// kernel.  Through cudaMemcpyAsync they would queue on the host->device copy engine BEHIND the previous step's heat-map
+// transfer (a copy engine serves its streams in issue order), and the step's own transfer — which needs the pixel boxes computed
+// from them — could not start until that transfer had drained: ~0.45 ms of idle link per step (profiles/r02_e2e_timeline.txt).
+struct PullSegs { int n; const uint32_t *src[8]; uint32_t *dst[8]; unsigned words[8]; };
+__global__ void __launch_bounds__(128)
+pull_segments_kernel(const __grid_constant__ PullSegs S)
+{
+    for (int k = 0; k < S.n; ++k)
+        for (unsigned i = blockIdx.x * 128u + threadIdx.x; i < S.words[k]; i += gridDim.x * 128u) S.dst[k][i] = __ldcs(S.src[k] + i);
+}
+
+int pull_segments_launch(int n, const void *const *src_mapped, void *const *dst, const size_t *bytes, cudaStream_t st)
+{
+    PullSegs S{};
+    S.n = n;
+    size_t most = 0;
+    for (int k = 0; k < n; ++k) {
+        S.src[k] = (const uint32_t *)src_mapped[k]; S.dst[k] = (uint32_t *)dst[k]; S.words[k] = (unsigned)(bytes[k] / 4);
+        if (bytes[k] > most) most = bytes[k];
+    }
+    const int ctas = (int)std::min<size_t>(16, std::max<size_t>(1, most / 4 / (128 * 4)));
+    JHN_TRY(prefer_max_carveout(pull_segments_kernel));
+    JHN_LAUNCH("pull_segments_kernel", st, pull_segments_kernel<<<ctas, 128, 0, st>>>(S));
     return JHN_OK;
 }
 

@@ -273,6 +273,61 @@ int heatmap_boxes_launch(const float *cam, const float *intr, const float *dist,
     return JHN_OK;
 }
 
+// jhn_heatmap_spans: per (frame set, camera, pixel row) the column range [lo, hi] the gather can touch — tighter than the box
+// (the voxel cube projects to a hexagon: the row spans hold 78 % of the box's pixels at the Example shape, and every index
+// the reference computes: tests).  A fine voxel's coordinates are rounded convex combinations of the 8 coarse corners of its
+// cell and (v / 2).int() is monotone, so its pixel lies inside the integer box of those corners: every cell adds its box's
+// columns to the rows its box covers.  Shared-memory atomics per (camera, slab of cells), one global atomic per row and block.
+// spans: int2 {lo, -hi} per row, minima of a buffer memset to 0x7f7f7f7f (rows no voxel maps to keep lo > hi).
+constexpr int SPAN_MAX_HS = 2048;
+__global__ void __launch_bounds__(256)
+row_spans_kernel(const float2 *__restrict__ cab, int ncam, int h, int hs, int i_per_block, int2 *__restrict__ spans)
+{
+    __shared__ int s_lo[SPAN_MAX_HS], s_nhi[SPAN_MAX_HS];
+    const int c = blockIdx.y, b = blockIdx.z;
+    for (int y = threadIdx.x; y < hs; y += blockDim.x) { s_lo[y] = 0x7f7f7f7f; s_nhi[y] = 0x7f7f7f7f; }
+    __syncthreads();
+    const float2 *src = cab + ((size_t)b * ncam + c) * h * h * h;
+    const int hc = h > 1 ? h - 1 : 1;                                   // cells per dimension (h == 1: one degenerate cell)
+    const int i1 = min((int)(blockIdx.x + 1) * i_per_block, hc);
+    for (int i = blockIdx.x * i_per_block; i < i1; ++i) {
+        const int ip = min(i + 1, h - 1);
+        for (int q = threadIdx.x; q < hc * hc; q += blockDim.x) {
+            const int j = q / hc, k = q - j * hc, jp = min(j + 1, h - 1), kp = min(k + 1, h - 1);
+            int x0 = 0x7fffffff, x1 = -0x7fffffff, y0 = 0x7fffffff, y1 = -0x7fffffff;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float2 v = __ldg(src + ((size_t)((e & 4) ? ip : i) * h + ((e & 2) ? jp : j)) * h + ((e & 1) ? kp : k));
+                const int px = __float2int_rz(__fmul_rn(v.x, 0.5f)), py = __float2int_rz(__fmul_rn(v.y, 0.5f));
+                x0 = min(x0, px); x1 = max(x1, px); y0 = min(y0, py); y1 = max(y1, py);
+            }
+            y0 = max(y0, 0); y1 = min(y1, hs - 1);
+            for (int y = y0; y <= y1; ++y) { atomicMin(s_lo + y, x0); atomicMin(s_nhi + y, -x1); }
+        }
+    }
+    __syncthreads();
+    int *g = reinterpret_cast<int *>(spans + ((size_t)b * ncam + c) * hs);
+    for (int y = threadIdx.x; y < hs; y += blockDim.x)
+        if (s_lo[y] != 0x7f7f7f7f) { atomicMin(g + 2 * y, s_lo[y]); atomicMin(g + 2 * y + 1, s_nhi[y]); }
+}
+
+int heatmap_spans_launch(const float *cam, const float *intr, const float *dist, const float *center3D, const int32_t *centerHM,
+                         int B, int ncam, int hs, int G, float spacing, void *scratch, int32_t *boxes, int32_t *spans, cudaStream_t st)
+{
+    const int h = G / 2;
+    if (hs > SPAN_MAX_HS) return fail(JHN_ERR_SHAPE, "jhn_heatmap_spans: maps of up to %d rows (got %d)", SPAN_MAX_HS, hs);
+    JHN_CUDA(cudaMemsetAsync(boxes, 0x7f, (size_t)B * ncam * sizeof(int4), st));
+    JHN_CUDA(cudaMemsetAsync(spans, 0x7f, (size_t)B * ncam * hs * sizeof(int2), st));
+    JHN_LAUNCH("coarse_project_kernel", st,
+               coarse_project_kernel<<<dim3(cdiv((long long)h * h * h, 256), B), 256,
+                                       ncam * (CP_PARAMS * sizeof(float) + 4 * sizeof(int)), st>>>(
+                   cam, intr, dist, center3D, centerHM, B, ncam, h, spacing, hs, (float2 *)scratch, (int *)boxes));
+    const int hc = h > 1 ? h - 1 : 1, ipb = 4;
+    JHN_LAUNCH("row_spans_kernel", st,
+               row_spans_kernel<<<dim3(cdiv(hc, ipb), ncam, B), 256, 0, st>>>((const float2 *)scratch, ncam, h, hs, ipb, (int2 *)spans));
+    return JHN_OK;
+}
+
 constexpr int TS = 8;                                   // voxel tile side
 constexpr int CS = TS / 2 + 2;                          // coarse corners per dimension needed by a tile
 

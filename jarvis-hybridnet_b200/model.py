@@ -245,7 +245,7 @@ class HybridNet3D(nn.Module):
                                   hres=torch.empty((B, self.K, 4), dtype=torch.float32, pin_memory=True),
                                   boxes=torch.empty((B, ncam, 4), dtype=torch.int32, device=dev),
                                   hboxes=torch.empty((B, ncam, 4), dtype=torch.int32, pin_memory=True),
-                                  pulled=torch.zeros(1, dtype=torch.int64, device=dev),
+                                  pulled=torch.zeros(1, dtype=torch.int64, device=dev), spans=None, cab=None,
                                   hpulled=torch.zeros(1, dtype=torch.int64).pin_memory(), busy=None, done=None))
             self._host = dict(key=key, slots=slots, n=0, copy=torch.cuda.Stream(device=dev, priority=-1),
                               aux=torch.cuda.Stream(device=dev, priority=-1))
@@ -260,11 +260,15 @@ class HybridNet3D(nn.Module):
         hm_h = host_inputs[0]
         roi = roi_upload if (roi_upload and hm_h.dtype in (torch.float16, torch.bfloat16) and hm_h.is_pinned()) else None
         pull_frac = 0.0
+        use_spans = False
         if isinstance(roi, str) and roi.startswith("hybrid"):          # "hybrid:0.25" = a quarter of every chunk's images by the pull kernel
-            pull_frac = float(roi.split(":")[1]) if ":" in roi else 0.25
+            pull_frac = float(roi.split(":")[1]) if ":" in roi else 0.6
+            # "hybrid-spans:f": the pull kernel moves each pixel row's column span (jhn_heatmap_spans) instead of the whole box:
+            # 22 % fewer bytes, but computing the spans costs the GPU more than the link gains (4.6 vs 4.16 ms per step, run 54)
+            use_spans = roi.startswith("hybrid-spans")
             roi = "hybrid"
         if roi not in (None, "pull", "dma", "hybrid"):
-            raise ValueError("roi_upload must be 'pull', 'dma', 'hybrid[:fraction]' or None")
+            raise ValueError("roi_upload must be 'pull', 'dma', 'hybrid[:fraction]', 'hybrid-spans[:fraction]' or None")
         if S["done"] is not None:
             copy_stream.wait_event(S["done"])            # the kernels of the slot's previous step are done with its device buffers
             aux.wait_event(S["done"])
@@ -276,17 +280,37 @@ class HybridNet3D(nn.Module):
             pix = hm_h.shape[4] * hm_h.element_size()
             img = hs * hs * pix
             with torch.cuda.stream(aux):                 # small tensors, boxes: off the copy stream so that it never drains
-                for d, h in zip(dbuf[1:], host_inputs[1:]):
-                    d.copy_(h, non_blocking=True)
-                    h2d += h.numel() * h.element_size()
+                small_h = [h.contiguous() for h in host_inputs[1:]]
+                if all(h.is_pinned() and (h.numel() * h.element_size()) % 4 == 0 for h in small_h) and len(small_h) <= 8:
+                    # one kernel reads them out of mapped host memory: cudaMemcpyAsync copies would queue on the copy
+                    # engine behind the previous step's heat maps and hold this step's boxes (and transfer) back
+                    n = len(small_h)
+                    arr = lambda vals, ty: (ty * n)(*vals)
+                    _lib.check(lib.jhn_pull_small(n, arr([h.data_ptr() for h in small_h], ctypes.c_void_p),
+                                                  arr([d.data_ptr() for d in dbuf[1:]], ctypes.c_void_p),
+                                                  arr([h.numel() * h.element_size() for h in small_h], ctypes.c_size_t),
+                                                  ctypes.c_void_p(aux.cuda_stream)))
+                    S["keep"] = small_h                  # the kernel reads these after the call returns
+                else:
+                    for d, h in zip(dbuf[1:], host_inputs[1:]):
+                        d.copy_(h, non_blocking=True)
+                h2d += sum(h.numel() * h.element_size() for h in small_h)
                 f = lambda t: t.contiguous().float()
                 c3, chm = f(dbuf[1]), dbuf[2].contiguous().to(torch.int32)
                 cam, intr, dist = f(dbuf[3]), f(dbuf[4]), f(dbuf[5])
-                _lib.check(lib.jhn_heatmap_boxes(_lib.dptr(cam), _lib.dptr(intr), _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm),
-                                                 B, ncam, hs, self.G, float(self.spacing), _lib.dptr(boxes),
-                                                 ctypes.c_void_p(aux.cuda_stream)))
+                if roi == "hybrid" and use_spans:        # boxes for the copy engine, per-row column spans for the pull kernel
+                    if S["spans"] is None:
+                        S["spans"] = torch.empty((B, ncam, hs, 2), dtype=torch.int32, device=dev)
+                        S["cab"] = torch.empty(B * ncam * (self.G // 2) ** 3 * 2, dtype=torch.float32, device=dev)
+                    _lib.check(lib.jhn_heatmap_spans(_lib.dptr(cam), _lib.dptr(intr), _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm),
+                                                     B, ncam, hs, self.G, float(self.spacing), _lib.dptr(S["cab"]), S["cab"].numel() * 4,
+                                                     _lib.dptr(boxes), _lib.dptr(S["spans"]), ctypes.c_void_p(aux.cuda_stream)))
+                else:
+                    _lib.check(lib.jhn_heatmap_boxes(_lib.dptr(cam), _lib.dptr(intr), _lib.dptr(dist), _lib.dptr(c3), _lib.dptr(chm),
+                                                     B, ncam, hs, self.G, float(self.spacing), _lib.dptr(boxes),
+                                                     ctypes.c_void_p(aux.cuda_stream)))
                 hboxes.copy_(boxes, non_blocking=True)
-                if roi == "pull":
+                if roi in ("pull", "hybrid"):
                     pulled.zero_()
                 small = torch.cuda.Event()
                 small.record(aux)
@@ -319,20 +343,21 @@ class HybridNet3D(nn.Module):
                     evs[-1].record(copy_stream)
                 if n_pull:
                     j0 = i0 + n_dma
-                    _lib.check(lib.jhn_pull_heatmap_boxes(ctypes.c_void_p(hm_h.data_ptr() + j0 * img), ctypes.c_void_p(dbuf[0].data_ptr() + j0 * img),
-                                                          ctypes.c_void_p(boxes.data_ptr() + j0 * 16), n_pull, hs, pix,
-                                                          _lib.dptr(pulled) if roi == "pull" else None, spull))
-                    if roi == "hybrid":                  # the host has the boxes: count the pulled bytes here
-                        b4 = hboxes.view(-1, 4)[j0:j0 + n_pull].to(torch.int64)
-                        h2d += int(((1 - b4[:, 2] - b4[:, 0]).clamp_(min=0) * (1 - b4[:, 3] - b4[:, 1]).clamp_(min=0)).sum()) * pix
+                    srcp, dstp = ctypes.c_void_p(hm_h.data_ptr() + j0 * img), ctypes.c_void_p(dbuf[0].data_ptr() + j0 * img)
+                    if roi == "hybrid" and use_spans:
+                        _lib.check(lib.jhn_pull_heatmap_spans(srcp, dstp, ctypes.c_void_p(S["spans"].data_ptr() + j0 * hs * 8), n_pull, hs, pix,
+                                                              _lib.dptr(pulled), spull))
+                    else:
+                        _lib.check(lib.jhn_pull_heatmap_boxes(srcp, dstp, ctypes.c_void_p(boxes.data_ptr() + j0 * 16), n_pull, hs, pix,
+                                                              _lib.dptr(pulled), spull))
                     evs.append(torch.cuda.Event())
                     evs[-1].record(ps)
                 events.append(evs)
-            if roi == "pull":
-                with torch.cuda.stream(copy_stream):
+            if roi in ("pull", "hybrid"):                # bytes the kernel moved: counted on the device, 8 bytes back
+                with torch.cuda.stream(ps):
                     hpulled.copy_(pulled, non_blocking=True)
                 done_copy = torch.cuda.Event()
-                done_copy.record(copy_stream)
+                done_copy.record(ps)
         else:
             with torch.cuda.stream(copy_stream):
                 for lo in range(0, B, chunk):
@@ -351,8 +376,8 @@ class HybridNet3D(nn.Module):
         hres.copy_(res, non_blocking=True)
         S["done"] = torch.cuda.Event()
         S["done"].record(main)
-        d2h = res.numel() * 4 + (boxes.numel() * 4 if roi else 0) + (8 if roi == "pull" else 0)
-        S["busy"] = _HostStep(S, h2d, d2h, done_copy, hpulled if roi == "pull" else None)
+        d2h = res.numel() * 4 + (boxes.numel() * 4 if roi else 0) + (8 if roi in ("pull", "hybrid") else 0)
+        S["busy"] = _HostStep(S, h2d, d2h, done_copy, hpulled if roi in ("pull", "hybrid") else None)
         return S["busy"]
 
 

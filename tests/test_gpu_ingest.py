@@ -155,3 +155,47 @@ def test_frame_uploader_round_trip():
         ev.synchronize()
         assert np.array_equal(got.cpu().numpy(), fr)
     assert up.bytes_per_upload == 2 * 3 * 16 * 16 * 3
+
+
+@pytest.mark.parametrize("hs,source", [(40, "host"), (256, "device"), (300, "host")])
+def test_pull_heatmap_spans_moves_exactly_the_row_spans(hs, source):
+    """jhn_pull_heatmap_spans (flat kernel for maps of <= 256 rows, warp-per-row kernel above) and jhn_pull_small:
+    arbitrary spans, rows without a span, a pinned host or a device tensor as the source; everything else stays untouched."""
+    import ctypes
+    from jarvis_hybridnet_b200 import _lib
+    lib = _lib.load()
+    n_img = 5
+    rng = np.random.default_rng(hs)
+    src = torch.from_numpy(rng.integers(1, 2 ** 15, size=(n_img, hs, hs, 24), dtype=np.int16))
+    src = src.pin_memory() if source == "host" else src.to(DEV)
+    dst = torch.full(src.shape, -7, dtype=torch.int16, device=DEV)
+    a, b = rng.integers(0, hs, size=(n_img, hs)), rng.integers(0, hs, size=(n_img, hs))
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    empty = rng.random((n_img, hs)) < 0.3
+    spans = np.stack([np.where(empty, 0x7f7f7f7f, lo), np.where(empty, 0x7f7f7f7f, -hi)], -1).astype(np.int32)
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for shape in ((128, 48, 8), (32, 3, 5)):
+        lib.jhn_debug_set_pull_config(*shape)
+        dst.fill_(-7); counter.zero_()
+        _lib.check(lib.jhn_pull_heatmap_spans(ctypes.c_void_p(src.data_ptr()), _lib.dptr(dst), _lib.dptr(torch.from_numpy(spans).to(DEV)),
+                                              n_img, hs, 48, _lib.dptr(counter), _lib.stream_ptr()))
+        want = np.full(src.shape, -7, np.int16)
+        s = src.cpu().numpy()
+        for i in range(n_img):
+            for y in range(hs):
+                if not empty[i, y]:
+                    want[i, y, lo[i, y]:hi[i, y] + 1] = s[i, y, lo[i, y]:hi[i, y] + 1]
+        assert np.array_equal(dst.cpu().numpy(), want)
+        assert int(counter.item()) == int(((hi - lo + 1) * ~empty).sum()) * 48
+    lib.jhn_debug_set_pull_config(128, 48, 8)
+    # jhn_pull_small: a few small pinned tensors by one kernel
+    hts = [torch.from_numpy(rng.standard_normal(n).astype(np.float32)).pin_memory() for n in (3, 96, 1, 4321)]
+    dts = [torch.zeros_like(t, device=DEV) for t in hts]
+    n = len(hts)
+    _lib.check(lib.jhn_pull_small(n, (ctypes.c_void_p * n)(*[t.data_ptr() for t in hts]), (ctypes.c_void_p * n)(*[t.data_ptr() for t in dts]),
+                                  (ctypes.c_size_t * n)(*[t.numel() * 4 for t in hts]), _lib.stream_ptr()))
+    for h, d in zip(hts, dts):
+        assert torch.equal(d.cpu(), h)
+    not_pinned = torch.zeros(4)
+    rc = lib.jhn_pull_small(1, (ctypes.c_void_p * 1)(not_pinned.data_ptr()), (ctypes.c_void_p * 1)(dts[0].data_ptr()), (ctypes.c_size_t * 1)(12), _lib.stream_ptr())
+    assert rc != 0 and b"not pinned" in lib.jhn_last_error()

@@ -116,21 +116,24 @@ def test_forward_host_uploads_only_the_pixel_boxes():
     assert h2d_full == full
     res, h2d, d2h = net.forward_host(host, chunk=2)                 # "dma": the boxes by strided copy-engine transfers
     assert torch.equal(res, want)
-    assert h2d < full and h2d > sum(t.numel() * t.element_size() for t in host[1:])
+    small = sum(t.numel() * t.element_size() for t in host[1:])
+    assert h2d < full and h2d > small
     res, h2d_pull, _ = net.forward_host(host, chunk=2, roi_upload="pull")  # boxes read out of mapped host memory by a kernel
     assert torch.equal(res, want) and h2d_pull == h2d
     # both at once: the copy engine takes the first images of every chunk, the pull kernel the rest; other launch shapes of the pull kernel
-    for mode, shape in (("hybrid:0.6", (128, 48, 8)), ("hybrid:0.25", (32, 7, 3)), ("hybrid:1.0", (64, 200, 1)), ("hybrid:0", (128, 48, 8))):
+    for mode, shape in (("hybrid:0.6", (128, 48, 8)), ("hybrid:0.25", (32, 7, 3)), ("hybrid:1.0", (64, 200, 1)), ("hybrid:0", (128, 48, 8)),
+                        ("hybrid-spans:0.6", (128, 48, 8)), ("hybrid-spans:1.0", (32, 9, 5)), ("hybrid-spans:0", (128, 48, 8))):
         _lib.load().jhn_debug_set_pull_config(*shape)
-        res, h2d_h, _ = net.forward_host(host, chunk=2, roi_upload=mode)
-        assert torch.equal(res, want) and h2d_h == h2d, mode
+        res, h2d_h, _ = net.forward_host(host, chunk=2, roi_upload=mode)      # "-spans": the pulled images move their row spans only
+        assert torch.equal(res, want), mode
+        assert small < h2d_h < h2d if mode.startswith("hybrid-spans") and not mode.endswith(":0") else h2d_h == h2d, mode
     _lib.load().jhn_debug_set_pull_config(128, 48, 8)
     # poison everything on the device, upload the boxes again: the gather must not see the poison
-    for mode in ("dma", "pull", "hybrid:0.5"):
+    for mode in ("dma", "pull", "hybrid:0.5", "hybrid-spans:0.5"):
         for slot in net._host["slots"]:
             slot["dbuf"][0].view(torch.int16).fill_(0x7e00)          # fp16 NaN
         res, h2d2, _ = net.forward_host(host, chunk=2, roi_upload=mode)
-        assert torch.equal(res, want) and h2d2 == h2d
+        assert torch.equal(res, want) and (small < h2d2 < h2d if mode.startswith("hybrid-spans") else h2d2 == h2d)
     # two steps in flight (double-buffered slots): same results, in order
     other = [host[0].flip(0).contiguous().pin_memory()] + [t.flip(0).contiguous().pin_memory() for t in host[1:]]
     a = net.forward_host_async(host, chunk=2)
@@ -153,6 +156,29 @@ def test_forward_host_uploads_only_the_pixel_boxes():
             x0, y0, x1, y1 = boxes[b, c, 0], boxes[b, c, 1], -boxes[b, c, 2], -boxes[b, c, 3]
             assert x.min() >= x0 and x.max() <= x1 and y.min() >= y0 and y.max() <= y1
             assert x1 - x0 <= (x.max() - x.min()) + 2 and y1 - y0 <= (y.max() - y.min()) + 2      # and they are tight
+    # jhn_heatmap_spans: the same boxes, and per pixel row a column range that holds every index of that row
+    lib = _lib.load()
+    bx2 = torch.empty((5, sh.ncam, 4), dtype=torch.int32, device=DEV)
+    spans = torch.empty((5, sh.ncam, hs, 2), dtype=torch.int32, device=DEV)
+    scratch = torch.empty(5 * sh.ncam * (net.G // 2) ** 3 * 2, dtype=torch.float32, device=DEV)
+    f = lambda t: t.contiguous().float()
+    _lib.check(lib.jhn_heatmap_spans(_lib.dptr(f(devt[3])), _lib.dptr(f(devt[4])), _lib.dptr(f(devt[5])), _lib.dptr(f(devt[1])),
+                                     _lib.dptr(devt[2].contiguous().to(torch.int32)), 5, sh.ncam, hs, net.G, float(net.spacing),
+                                     _lib.dptr(scratch), scratch.numel() * 4, _lib.dptr(bx2), _lib.dptr(spans), _lib.stream_ptr()))
+    assert np.array_equal(bx2.cpu().numpy(), boxes)
+    sp = spans.cpu().numpy()
+    lo, hi = sp[..., 0], -sp[..., 1]
+    span_px = box_px = 0
+    for b in range(5):
+        for c in range(sh.ncam):
+            x, y = idx[b, c] % hs, idx[b, c] // hs
+            assert (x >= lo[b, c][y]).all() and (x <= hi[b, c][y]).all()
+            rows = hi[b, c] >= lo[b, c]
+            assert rows.sum() == -boxes[b, c, 3] - boxes[b, c, 1] + 1                                 # exactly the box's rows
+            assert lo[b, c][rows].min() == boxes[b, c, 0] and hi[b, c][rows].max() == -boxes[b, c, 2]
+            span_px += int((hi[b, c] - lo[b, c] + 1)[rows].sum())
+            box_px += int((-boxes[b, c, 2] - boxes[b, c, 0] + 1) * (-boxes[b, c, 3] - boxes[b, c, 1] + 1))
+    assert span_px < box_px
 
 
 @pytest.mark.parametrize("name", V2V_CASES)

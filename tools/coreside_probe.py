@@ -30,15 +30,16 @@ bx = boxes.cpu().view(-1, 4)
 nbytes = int(((1 - bx[:, 2] - bx[:, 0]) * (1 - bx[:, 3] - bx[:, 1])).clamp_(min=0).sum()) * pix
 dst = torch.zeros_like(dev[0])
 sa, sb = torch.cuda.Stream(), torch.cuda.Stream(priority=int(os.environ.get("PULL_PRIO", "0")))
-NF, NP = 10, 6
+NF, NP = 10, int(os.environ.get('PULL_REPS', '6'))
 
 def fwd():
     with torch.cuda.stream(sa):
         for _ in range(NF): net(*dev)
+SRC = dev[0] if os.environ.get("PULL_FROM_DEVICE") else host[0]     # PULL_FROM_DEVICE=1: same kernel, no PCIe — separates SM co-residency from link effects
 def pull():
     with torch.cuda.stream(sb):
         for _ in range(NP):
-            _lib.check(lib.jhn_pull_heatmap_boxes(ctypes.c_void_p(host[0].data_ptr()), ctypes.c_void_p(dst.data_ptr()), _lib.dptr(boxes), B * ncam, hs, pix, None,
+            _lib.check(lib.jhn_pull_heatmap_boxes(ctypes.c_void_p(SRC.data_ptr()), ctypes.c_void_p(dst.data_ptr()), _lib.dptr(boxes), B * ncam, hs, pix, None,
                                                   ctypes.c_void_p(sb.cuda_stream)))
 def timed(fa, fb):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -67,3 +68,23 @@ for spec in sys.argv[1:]:
         _lib.profile(True); timed(fwd, pull); k = _lib.profile_collect(); _lib.profile(False)
         print("   ", {n: round(v[1] / NF, 3) for n, v in sorted(k.items(), key=lambda kv: -kv[1][1]) if n != "pull_boxes_kernel"}, flush=True)
     print(json.dumps(dict(spec=spec, pull_alone_GBps=round(alone, 1), forward_ms_with_pull=round(both[0], 3), pull_GBps_with_forward=round(both[1], 1))), flush=True)
+
+# ---- what does a CTA that merely sits on an SM cost?  (tools/coreside_dummy.cu, built with nvcc into tools/libcoreside_dummy.so)
+so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcoreside_dummy.so")
+if os.environ.get("PROBE_DUMMY") and os.path.exists(so):
+    dl = ctypes.CDLL(so)
+    dl.dummy_launch.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    scratch = torch.zeros(64 << 20, dtype=torch.uint8, device="cuda")
+    for mode, name, carve in ((0, "sleep", -1), (0, "sleep", 100), (0, "sleep", 50)):
+        assert dl.dummy_set_carveout(carve) == 0
+        name = f"{name} carveout {carve}"
+        for ctas, thr in ((48, 128), (148, 128)):
+            def dummy():
+                rc = dl.dummy_launch(ctas, thr, mode, 60000.0, ctypes.c_void_p(scratch.data_ptr()), scratch.numel() // 16, ctypes.c_void_p(sb.cuda_stream))
+                assert rc == 0, rc
+            both = timed(fwd, dummy)
+            print(json.dumps(dict(dummy=name, ctas=ctas, threads=thr, forward_ms_next_to_it=round(both[0], 3))), flush=True)
+            torch.cuda.synchronize()
+            if os.environ.get("PROBE_KERNELS"):
+                _lib.profile(True); timed(fwd, dummy); k = _lib.profile_collect(); _lib.profile(False)
+                print("   ", {n: round(v[1] / NF, 3) for n, v in sorted(k.items(), key=lambda kv: -kv[1][1])}, flush=True)

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+PROBE_KERNELS=1 PROBE_DUMMY=1 timeout -s KILL 300 python tools/coreside_probe.py 2>&1 | tail -12 | tee gpurun_out/r2_run50.txt
