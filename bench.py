@@ -614,18 +614,25 @@ def main():
     # (bound by the link), both at once; chunk = the whole batch.  JHN_E2E_UPLOAD=dma JHN_E2E_CHUNK=8 is the copy-engine-only path.
     e2e_upload = os.environ.get("JHN_E2E_UPLOAD", "hybrid:0.6" if precision == "bf16" else "dma")
     e2e_chunk = int(os.environ.get("JHN_E2E_CHUNK", str(B) if e2e_upload.startswith("hybrid") else "8"))
-    # Steps are pipelined two deep, as a prediction loop with a prefetching loader runs them: step i+1 is submitted
-    # (forward_host_async: its uploads queue behind step i's on the copy stream) before step i's result is collected, so the
-    # link stays busy while step i computes.  Every step uploads its own inputs and downloads its own result inside the region.
+    # Steps are pipelined, as a prediction loop with a prefetching loader runs them: up to `e2e_ahead` later steps are submitted
+    # (forward_host_async: their uploads queue behind the running step's on the copy / pull streams) before a step's result is
+    # collected, so the link stays busy while that step computes.  Every step uploads its own inputs and downloads its own result
+    # inside the region.  Two steps ahead (three sets of device buffers) make the step time insensitive to the copy-engine /
+    # pull-kernel split (4.15 - 4.27 ms for fractions 0.5 - 0.7; one step ahead: 4.0 - 4.8; profiles/r02_e2e_hybrid_upload.txt).
+    from collections import deque
+    e2e_ahead = int(os.environ.get("JHN_E2E_AHEAD", "2"))
+    submit = lambda i: net.forward_host_async(host_cl[i % n_pool], chunk=e2e_chunk, roi_upload=e2e_upload, slots=e2e_ahead + 1)
     for i in range(max(min(W, 3), 2)):
-        net.forward_host_async(host_cl[i % n_pool], chunk=e2e_chunk, roi_upload=e2e_upload).result()
+        submit(i).result()
     barrier()
     t0 = time.perf_counter()
-    pending = net.forward_host_async(host_cl[0], chunk=e2e_chunk, roi_upload=e2e_upload)
-    for i in range(1, K_steps + 1):
-        nxt = net.forward_host_async(host_cl[i % n_pool], chunk=e2e_chunk, roi_upload=e2e_upload) if i < K_steps else None
-        res, h2d, d2h = pending.result()
-        pending = nxt
+    inflight = deque()
+    for i in range(K_steps):
+        inflight.append(submit(i))
+        if len(inflight) > e2e_ahead:
+            res, h2d, d2h = inflight.popleft().result()
+    while inflight:
+        res, h2d, d2h = inflight.popleft().result()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device="cuda")
@@ -637,7 +644,7 @@ def main():
                d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * e2e_s / K_steps,
                heatmap_format="fp16 channels-last (JHN_HM_F16_CL)" if precision == "bf16" else "fp32 planar",
                upload="per-camera pixel boxes of the voxel grid only (jhn_heatmap_boxes; %s: jhn_upload_heatmap_boxes = copy engine, "
-                      "jhn_pull_heatmap_boxes = kernel reading the pinned host tensor), chunk %d, steps pipelined two deep" % (e2e_upload, e2e_chunk))
+                      "jhn_pull_heatmap_boxes = kernel reading the pinned host tensor), chunk %d, up to %d steps submitted ahead" % (e2e_upload, e2e_chunk, e2e_ahead))
 
     # ---- B=1 latency (the reference's predictor runs one frame set per call): eager launches vs CUDA-graph replay ----
     latency = None

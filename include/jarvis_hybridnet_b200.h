@@ -163,6 +163,11 @@ int jhn_pull_heatmap_spans(const void *host_heatmaps, void *device_heatmaps, con
  *                             reads mapped host memory: unlike cudaMemcpyAsync they do not queue on the host->device copy
  *                             engine behind a large transfer issued earlier on another stream.  bytes[k] % 4 == 0. */
 int jhn_pull_small(int n, const void *const *host_tensors, void *const *device_tensors, const size_t *bytes, jhn_stream_t stream);
+/*   jhn_set_transfer_overlap  announces (1) / withdraws (0), for the CALLING THREAD, that forwards launched from now on run
+ *                             next to jhn_pull_* transfers: the 3x3x3 layers are then launched in their 120-register build,
+ *                             which leaves room on every SM for the transfer kernel's CTAs (5 % slower alone, but a forward
+ *                             that overlaps a pull otherwise runs those layers in two waves).  Results are identical. */
+void jhn_set_transfer_overlap(int on);
 /*   jhn_debug_set_pull_config tuning hook: launch shape of the pull kernel — threads per CTA (32, 64, 96 or 128), number of
  *                             CTAs, parts per image; an argument <= 0 leaves that value unchanged. */
 void jhn_debug_set_pull_config(int threads, int ctas, int split);

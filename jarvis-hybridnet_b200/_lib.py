@@ -56,6 +56,7 @@ SYMBOLS = {
     "jhn_debug_set_gather_box_bytes": (c_int, [c_int]),
     "jhn_debug_set_pull_config": (None, [c_int, c_int, c_int]),
     "jhn_pull_small": (c_int, [c_int, _P, _P, _P, _P]),
+    "jhn_set_transfer_overlap": (None, [c_int]),
     "jhn_heatmap_spans": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, c_size_t, _P, _P, _P]),
     "jhn_pull_heatmap_spans": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
 }

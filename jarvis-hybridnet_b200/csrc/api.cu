@@ -90,6 +90,7 @@ unsigned long long jhn_launch_count(void) { return g_launches.load(std::memory_o
 void jhn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 int jhn_debug_set_gather_box_bytes(int bytes) { return gather_set_box_bytes(bytes); }
 void jhn_debug_set_pull_config(int threads, int ctas, int split) { pull_set_config(threads, ctas, split); }
+void jhn_set_transfer_overlap(int on) { c3_set_transfer_overlap(on); }
 
 // Frame sets per internal pass of jhn_hybrid3d_forward.  Default: the whole batch in one pass.  Passes of 8 keep a
 // convolution's input + output (2 x 42 MB at the Example shape) inside the 126 MB L2, but measured on the B200 that buys

@@ -97,6 +97,7 @@ int heatmap_boxes_launch(const float *cam, const float *intr, const float *dist,
                          int B, int ncam, int hs, int G, float spacing, int32_t *boxes, cudaStream_t st);
 
 void pull_set_config(int threads, int ctas, int split);
+void c3_set_transfer_overlap(int on);   // conv3_tc.cu: thread-local, read when a 3x3x3 layer is launched
 int pull_spans_launch(const void *host_mapped, void *dev, const int32_t *spans, int n_images, int hs, int pixel_bytes,
                       unsigned long long *bytes_out, cudaStream_t st);
 int heatmap_spans_launch(const float *cam, const float *intr, const float *dist, const float *center3D, const int32_t *centerHM,

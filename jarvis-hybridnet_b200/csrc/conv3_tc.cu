@@ -67,17 +67,16 @@ __device__ __forceinline__ void c3_ld8x3(uint32_t t0, uint32_t t1, uint32_t t2, 
         : "memory");
 }
 
-// Register cap of the 480-thread configuration (NOUT <= 48, EW = 3): 120 instead of the 128 that __launch_bounds__(480) lets
-// ptxas take.  15 warps x 120 registers leave 1024 registers free in every scheduler partition of the SM — what one warp of
-// the 32-register host-memory pull kernel (jhn_pull_heatmap_boxes) needs.  With 128 the pull CTAs and this kernel's CTAs keep
-// each other off an SM, and a forward that overlaps a transfer runs the 3x3x3 layers in two waves (tools/coreside_probe.py).
-// A thread bound cannot express 120 (544 threads = 5 warps per partition -> 96), hence __maxnreg__.
-#ifndef C3_MAXNREG_480
-#define C3_MAXNREG_480 120
-#endif
+// Two builds of the 480-thread configuration (NOUT <= 48, EW = 3).  MAXR = 128 is the fastest (0.75 ms per 32 frame sets for the
+// six layers).  MAXR = 120 (0.79 ms) leaves 1024 registers free in every scheduler partition of the SM: room for one warp of
+// the 32-register host-memory pull kernel (jhn_pull_heatmap_boxes) per partition.  With 128 the pull CTAs and this kernel's CTAs
+// keep each other off an SM and a forward that overlaps a transfer runs the 3x3x3 layers in two waves; the launcher picks the
+// 120-register build while the calling thread has announced an overlapping transfer (jhn_set_transfer_overlap; run 60:
+// resident 10.32 k vs 10.19 k frame-sets/s, end to end 6.9 k vs 7.65 k).  A thread bound cannot express 120 (544 threads =
+// 5 warps per partition -> 96), hence __maxnreg__.
 // EW = epilogue warps per TMEM lane quadrant; each owns NOUT / EW output channels
-template <int NOUT, int EW>
-__global__ void __maxnreg__(96 + 128 * EW == 480 ? C3_MAXNREG_480 : 168)
+template <int NOUT, int EW, int MAXR>
+__global__ void __maxnreg__(MAXR)
 tc_conv3_kernel(const C3Launch L)
 {
     constexpr int C3_THREADS = 96 + 128 * EW;
@@ -422,7 +421,10 @@ int c3_pack(const float *src, __nv_bfloat16 *dst, int cout, int cin, int NOUT, c
     return JHN_OK;
 }
 
-template <int NOUT, int EW>
+static thread_local int t_transfer_overlap = 0;
+void c3_set_transfer_overlap(int on) { t_transfer_overlap = on ? 1 : 0; }
+
+template <int NOUT, int EW, int MAXR>
 static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st)
 {
     // the attribute is per (function, device): one bit per device, set on first use, safe from any thread
@@ -433,10 +435,10 @@ static int c3_launch_t(const C3Launch &L, int grid, size_t smem, cudaStream_t st
     if (!(configured.load(std::memory_order_acquire) & bit)) {
         int max_smem = 0;
         JHN_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        JHN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<NOUT, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        JHN_CUDA(cudaFuncSetAttribute(tc_conv3_kernel<NOUT, EW, MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         configured.fetch_or(bit, std::memory_order_release);
     }
-    JHN_LAUNCH("tc_conv3_stacked", st, tc_conv3_kernel<NOUT, EW><<<grid, 96 + 128 * EW, smem, st>>>(L));
+    JHN_LAUNCH("tc_conv3_stacked", st, tc_conv3_kernel<NOUT, EW, MAXR><<<grid, 96 + 128 * EW, smem, st>>>(L));
     return JHN_OK;
 }
 
@@ -458,11 +460,11 @@ int c3_launch(int NOUT, const void *in, const __nv_bfloat16 *w, const float *bia
     if (stats) { stats->grid = grid; stats->Tb = L.NT * D; stats->T = L.total_tiles; L.stats = *stats; }
     else L.stats = StatPart{nullptr, 0, 0, 0};
     switch (NOUT) {
-    case 16: return c3_launch_t<16, 2>(L, grid, smem, st);
-    case 32: return c3_launch_t<32, 2>(L, grid, smem, st);
-    case 48: return c3_launch_t<48, C3_EW48>(L, grid, smem, st);
-    case 64: return c3_launch_t<64, 2>(L, grid, smem, st);
-    case 80: return c3_launch_t<80, 2>(L, grid, smem, st);
+    case 16: return c3_launch_t<16, 2, 168>(L, grid, smem, st);
+    case 32: return c3_launch_t<32, 2, 168>(L, grid, smem, st);
+    case 48: return t_transfer_overlap ? c3_launch_t<48, C3_EW48, 120>(L, grid, smem, st) : c3_launch_t<48, C3_EW48, 128>(L, grid, smem, st);
+    case 64: return c3_launch_t<64, 2, 168>(L, grid, smem, st);
+    case 80: return c3_launch_t<80, 2, 168>(L, grid, smem, st);
     }
     return fail(JHN_ERR_SHAPE, "stacked 3x3x3 kernel: unsupported channel width %d", NOUT);
 }

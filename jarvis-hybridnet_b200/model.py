@@ -367,12 +367,19 @@ class HybridNet3D(nn.Module):
                     ev.record(copy_stream)
                     events.append([ev])
             h2d = sum(t.numel() * t.element_size() for t in host_inputs)
-        for i, lo in enumerate(range(0, B, chunk)):
-            for ev in events[i]:
-                main.wait_event(ev)
-            pts, conf, _ = self.forward(*[d[lo:lo + chunk] for d in dbuf])
-            res[lo:lo + chunk, :, :3] = pts
-            res[lo:lo + chunk, :, 3] = conf
+        overlap = roi in ("pull", "hybrid")              # these forwards run next to pull kernels: see jhn_set_transfer_overlap
+        if overlap:
+            lib.jhn_set_transfer_overlap(1)
+        try:
+            for i, lo in enumerate(range(0, B, chunk)):
+                for ev in events[i]:
+                    main.wait_event(ev)
+                pts, conf, _ = self.forward(*[d[lo:lo + chunk] for d in dbuf])
+                res[lo:lo + chunk, :, :3] = pts
+                res[lo:lo + chunk, :, 3] = conf
+        finally:
+            if overlap:
+                lib.jhn_set_transfer_overlap(0)
         hres.copy_(res, non_blocking=True)
         S["done"] = torch.cuda.Event()
         S["done"].record(main)

@@ -94,6 +94,14 @@ def test_forward_host_pipelined_equals_forward():
             assert torch.equal(res, want)                            # same partition -> same bits
     pts2, conf2, _ = net(*devt)
     assert torch.equal(pts2, pts) and torch.equal(conf2, conf)      # run to run: bit-identical
+    # the 120-register build of the 3x3x3 layers (launched while a transfer overlap is announced) computes the same bits
+    from jarvis_hybridnet_b200 import _lib
+    _lib.load().jhn_set_transfer_overlap(1)
+    try:
+        pts3, conf3, _ = net(*devt)
+    finally:
+        _lib.load().jhn_set_transfer_overlap(0)
+    assert torch.equal(pts3, pts) and torch.equal(conf3, conf)
 
 
 def test_forward_host_uploads_only_the_pixel_boxes():

@@ -53,6 +53,7 @@ def timed(fa, fb):
     torch.cuda.synchronize()
     return (ev[0].elapsed_time(ev[1]) / NF if fa else None, nbytes * NP / (ev[2].elapsed_time(ev[3]) * 1e6) if fb else None)
 
+lib.jhn_set_transfer_overlap(int(os.environ.get("PROBE_OVERLAP", "1")))     # 1: the 120-register build of the 3x3x3 layers
 fwd(); torch.cuda.synchronize()
 print(json.dumps(dict(forward_alone_ms=round(timed(fwd, None)[0], 3), box_MB=round(nbytes / 1e6, 1))), flush=True)
 if os.environ.get("PROBE_KERNELS"):

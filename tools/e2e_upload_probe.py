@@ -1,7 +1,7 @@
 """End-to-end step time (host buffers in, [B,K,4] back) under different upload strategies:
 dma (copy engine, strided boxes), pull (kernel reading mapped host memory), hybrid:f (both at once, fraction f by the kernel),
 each with a launch shape of the pull kernel (threads per CTA, CTAs, parts per image).
-Usage: python tools/e2e_upload_probe.py "dma" "pull/32/296/8" "hybrid:0.3/32/296/8/16" ...   (mode/threads/ctas/split/chunk/steps-ahead)"""
+Usage: python tools/e2e_upload_probe.py "dma" "pull/32/296/8" "hybrid:0.3/32/296/8/16" ...   (mode/threads/ctas/split/chunk/steps-ahead/slots)"""
 import json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -29,9 +29,10 @@ for spec in sys.argv[1:]:
     thr, ctas, split = (int(x) for x in parts[1:4]) if len(parts) >= 4 else (128, 48, 8)
     chunk = int(parts[4]) if len(parts) >= 5 else 8
     ahead = int(parts[5]) if len(parts) >= 6 else 1
+    nslots = int(parts[6]) if len(parts) >= 7 else ahead + 1
     lib.jhn_debug_set_pull_config(thr, ctas, split)
     for i in range(3):
-        out = net.forward_host_async(host[i % 2], chunk=chunk, roi_upload=mode, slots=ahead + 1).result()[0].clone()
+        out = net.forward_host_async(host[i % 2], chunk=chunk, roi_upload=mode, slots=nslots).result()[0].clone()
     if ref is None:
         ref = out
     same = float((ref - out).abs().max())
@@ -39,7 +40,7 @@ for spec in sys.argv[1:]:
     torch.cuda.synchronize(); t0 = time.perf_counter()
     q = deque()
     for i in range(K_steps):
-        q.append(net.forward_host_async(host[i % 2], chunk=chunk, roi_upload=mode, slots=ahead + 1))
+        q.append(net.forward_host_async(host[i % 2], chunk=chunk, roi_upload=mode, slots=nslots))
         if len(q) > ahead:
             res, h2d, d2h = q.popleft().result()
     while q:

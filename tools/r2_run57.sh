@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 500 python tools/e2e_upload_probe.py dma hybrid:0.5/128/48/8/32/1 hybrid:0.6/128/48/8/32/1 hybrid:0.7/128/48/8/32/1 hybrid:0.5/128/48/8/32/1 hybrid:0.6/128/48/8/32/1 hybrid:0.7/128/48/8/32/1 hybrid:0.6/128/32/8/32/1 hybrid:0.6/128/64/8/32/1 hybrid:0.6/128/48/8/16/1 pull/128/48/8/32/2 2>&1 | tail -12 | tee gpurun_out/r2_run57.txt
