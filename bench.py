@@ -612,7 +612,10 @@ def main():
     # Upload strategy (HybridNet3D.forward_host_async): "hybrid:0.6" = the copy engine moves 40 % of every chunk's per-camera pixel
     # boxes (strided DMA, bound by rows per second), the pull kernel reads the other 60 % straight out of the pinned host tensor
     # (bound by the link), both at once; chunk = the whole batch.  JHN_E2E_UPLOAD=dma JHN_E2E_CHUNK=8 is the copy-engine-only path.
-    e2e_upload = os.environ.get("JHN_E2E_UPLOAD", "hybrid:0.6" if precision == "bf16" else "dma")
+    # Up to 4 ranks per host; with 8 the ranks' transfers together hit the host's memory / PCIe fabric (~190 GB/s on this pool's
+    # boxes) and the copy engine alone is the more frugal client there: 8 GPUs 35.1 k frame-sets/s with "dma" against 31.8 k with
+    # the hybrid, 4 GPUs 25.5 k against 27.5 k (profiles/r02_run64_8gpu_*.json, r02_run66_4gpu_*.json).
+    e2e_upload = os.environ.get("JHN_E2E_UPLOAD", "hybrid:0.6" if precision == "bf16" and world <= 4 else "dma")
     e2e_chunk = int(os.environ.get("JHN_E2E_CHUNK", str(B) if e2e_upload.startswith("hybrid") else "8"))
     # Steps are pipelined, as a prediction loop with a prefetching loader runs them: up to `e2e_ahead` later steps are submitted
     # (forward_host_async: their uploads queue behind the running step's on the copy / pull streams) before a step's result is
@@ -620,7 +623,7 @@ def main():
     # inside the region.  Two steps ahead (three sets of device buffers) make the step time insensitive to the copy-engine /
     # pull-kernel split (4.15 - 4.27 ms for fractions 0.5 - 0.7; one step ahead: 4.0 - 4.8; profiles/r02_e2e_hybrid_upload.txt).
     from collections import deque
-    e2e_ahead = int(os.environ.get("JHN_E2E_AHEAD", "2"))
+    e2e_ahead = int(os.environ.get("JHN_E2E_AHEAD", "2" if e2e_upload.startswith("hybrid") else "1"))
     submit = lambda i: net.forward_host_async(host_cl[i % n_pool], chunk=e2e_chunk, roi_upload=e2e_upload, slots=e2e_ahead + 1)
     for i in range(max(min(W, 3), 2)):
         submit(i).result()
