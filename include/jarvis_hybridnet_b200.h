@@ -87,7 +87,8 @@ void jhn_profile_enable(int on);
 int jhn_profile_collect(char *buf, int cap);
 int jhn_debug_set_gather_box_bytes(int bytes);
 /* Frame sets per internal pass of jhn_hybrid3d_forward (0 = library default, which keeps the activations of one pass
- * inside the 126 MB L2).  Results do not depend on it.  Returns the value in effect. */
+ * inside the 126 MB L2).  Frame sets are independent; on the bf16 path the split changes how a sample's InstanceNorm partial sums
+ * are grouped (fp32 re-association, <= 5e-3 mm on the key points; bit-identical for equal splits).  Returns the value in effect. */
 int jhn_set_sub_batch(int frame_sets);
 
 /* ------------------------------------------------------------------------------------------------

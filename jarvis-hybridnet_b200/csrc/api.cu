@@ -96,7 +96,8 @@ void jhn_set_transfer_overlap(int on) { c3_set_transfer_overlap(on); }
 // convolution's input + output (2 x 42 MB at the Example shape) inside the 126 MB L2, but measured on the B200 that buys
 // nothing (profiles/r02_run1_subbatch.txt: 32 -> 3.36 ms, 16 -> 3.58, 8 -> 4.02, 4 -> 4.91 ms per 32 frame sets): the
 // persistent kernels lose more to their shorter tile ranges than the normalisation passes gain.  The knob stays for
-// callers that must bound the workspace.  Frame sets are independent, so results do not depend on it.
+// callers that must bound the workspace.  Frame sets are independent; on the bf16 path the split changes how a sample's
+// InstanceNorm partial sums are grouped (fp32 re-association, <= 5e-3 mm on the key points; bit-identical for equal splits).
 static std::atomic<int> g_sub_batch{1 << 20};
 int jhn_set_sub_batch(int n)
 {
