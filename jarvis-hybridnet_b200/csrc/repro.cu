@@ -760,15 +760,14 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
                 }
                 uint4 w[4][3];
                 if (fits) {
+                    // no per-voxel predicate here: a voxel of this lane that lies outside the grid (x / y edge tiles) still has
+                    // clamped corners, so its offset is inside the box; what it accumulates is never stored.  (The predicated
+                    // form cost 48 register-zeroing instructions per camera step.)
                     const uint8_t *box = gsm + bx.z;
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
-                        if (vi[v >> 1] && vj[v & 1]) {
-                            const uint4 *pp = reinterpret_cast<const uint4 *>(box + off[v]);
-                            w[v][0] = pp[0]; w[v][1] = pp[1]; w[v][2] = pp[2];
-                        } else {
-                            w[v][0] = w[v][1] = w[v][2] = make_uint4(0, 0, 0, 0);
-                        }
+                        const uint4 *pp = reinterpret_cast<const uint4 *>(box + off[v]);
+                        w[v][0] = pp[0]; w[v][1] = pp[1]; w[v][2] = pp[2];
                     }
                 } else {
                     const uint8_t *gbase = reinterpret_cast<const uint8_t *>(hm) + ((size_t)b * ncam + c) * hs * hs * G_PIX_BYTES;
