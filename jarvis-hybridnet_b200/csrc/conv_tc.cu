@@ -210,18 +210,21 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
         // (16-byte units) | LBO << 16, hi = SBO (= 8 units, 128 B) | version 1.
         const uint32_t lbo_a = (uint32_t)P.PB, lbo_b = (uint32_t)P.NOUT;           // in 16-byte units
         const uint32_t tap_units = (uint32_t)tap_bytes >> 4;
+        // the TC_PIPES issuer warps fill the tables together (each entry written once) and meet on a named barrier: every
+        // reader is then ordered after every writer by a barrier the whole group took part in
+        const int iw = warp - TC_PIPES;
         int n_mma = 0;
         for (int s = 0; s < P.nstages; ++s) {
-            if (lane == 0) stage_first[s] = n_mma;
+            if (iw == 0 && lane == 0) stage_first[s] = n_mma;
             n_mma += P.st[s].ntaps * (P.KC / 2);
         }
-        if (lane == 0) stage_first[P.nstages] = n_mma;
+        if (iw == 0 && lane == 0) stage_first[P.nstages] = n_mma;
         {
             const uint32_t a_lo_c = lbo_a << 16, b_lo_c = lbo_b << 16;
             const uint32_t w_units = smem_u32(w_smem) >> 4, ring_units = smem_u32(ring) >> 4;
             const uint32_t slot_units = (uint32_t)P.stage_bytes >> 4, a_units = (uint32_t)P.stage_bytes_a >> 4;
             const int kpt = P.KC / 2;
-            for (int i = lane; i < n_mma * P.nslots; i += 32) {
+            for (int i = iw * 32 + lane; i < n_mma * P.nslots; i += 32 * TC_PIPES) {
                 const int slot = i / n_mma;
                 int e = i - slot * n_mma, s = 0;
                 while (e >= P.st[s].ntaps * kpt) { e -= P.st[s].ntaps * kpt; ++s; }
@@ -234,7 +237,7 @@ tc_conv_kernel(const __grid_constant__ TcProgram P, const TcLaunch L)
                                           b_lo_c | (b0 + wsel * tap_units + kc * lbo_b));
             }
         }
-        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_PIPES) : "memory");
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(P.NOUT);
             const uint64_t hi_c = (uint64_t)(8u | (1u << 14)) << 32;

@@ -534,6 +534,9 @@ constexpr int GCK = GC + 1, GCN = GC * GC * GCK;                               /
 #ifndef GS_SLOTS_V
 #define GS_SLOTS_V 4
 #endif
+#ifndef GS_LANE_ARRIVE
+#define GS_LANE_ARRIVE 1
+#endif
 constexpr int GS_PROD = 4, GS_SLOTS = GS_SLOTS_V, GS_THREADS = 32 * (4 + GS_PROD);  // 4 producer warps, 4 gather warps, GS_SLOTS box slots
 constexpr int GS_META = GCN * 8, GS_HDR = GS_META + 16;                        // header: corners (1200 B), then the int4 box
 constexpr int GS_CORNERS_PER_LANE = (GCN + 31) / 32;
@@ -581,7 +584,7 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < GS_SLOTS; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 4); }
+        for (int i = 0; i < GS_SLOTS; ++i) { mbar_init(smem_u32(full + i), GS_LANE_ARRIVE ? 32 : 1); mbar_init(smem_u32(empty + i), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -673,11 +676,15 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
             const uint32_t fb = smem_u32(full + slot);
             if (reuse) mbar_wait_parked(smem_u32(empty + slot), ph ^ 1u);      // item n - GS_SLOTS is done: slot + older header free
             __syncwarp();                                                      // every lane's corner copies + the box precede the arrive
+            // GS_LANE_ARRIVE: every producer lane arrives on the full barrier itself (count 32), i.e. each lane RELEASES its own
+            // cp.async corner copies instead of handing them to lane 0 through __syncwarp — the same ordering, but in the form
+            // compute-sanitizer's racecheck models (it reported the one-arrival form as a write / read hazard on the header).
             if (pitch == 0) {
-                if (lane == 0) mbar_arrive(fb);                                // box too large: gathered from global memory
+                if (GS_LANE_ARRIVE || lane == 0) mbar_arrive(fb);              // box too large: gathered from global memory
             } else {
                 const uint32_t row_bytes = (uint32_t)(bw * G_PIX_BYTES);
                 if (lane == 0) mbar_expect_tx(fb, row_bytes * (uint32_t)bh);
+                else if (GS_LANE_ARRIVE) mbar_arrive(fb);
                 __syncwarp();
                 const int tl = n / ncam, c = n - tl * ncam;
                 const int b = ((int)blockIdx.x + tl * (int)gridDim.x) / tiles_fs;
