@@ -91,6 +91,37 @@ def reproject_indices(center3D, centerHM, cameraMatrices, intrinsicMatrices, dis
     return (idx, ca, cb) if return_coarse else idx
 
 
+def pixel_boxes_and_row_spans(coarse_x, coarse_y, hs):
+    """What a host-buffer caller may upload instead of whole heat maps (no counterpart in the reference, which uploads everything):
+    per camera the pixel box {x0, y0, x1, y1} of the voxel grid and, per pixel row, the column range [lo, hi] (lo > hi: no voxel maps
+    to the row).  coarse_x / coarse_y: [ncam,h,h,h] coarse projections (`reproject_indices(..., return_coarse=True)`).
+
+    A fine voxel's (x, y) is a chain of rounded convex combinations of the 8 coarse corners of its cell (ATen's trilinear upsample,
+    repro_layer.py:78-81) and (v / 2).int() (:82-83) is monotone, so its pixel lies inside the integer box of those 8 corners: every
+    cell adds the columns of its box to the rows its box covers; the camera's box is the union."""
+    ca, cb = _f32(coarse_x), _f32(coarse_y)
+    ncam, h = ca.shape[0], ca.shape[1]
+    px, py = np.trunc(ca * np.float32(0.5)).astype(np.int64), np.trunc(cb * np.float32(0.5)).astype(np.int64)
+
+    def cells(a, f):                                   # reduce over the 8 corners of every cell (a single point: one degenerate cell)
+        for ax in (1, 2, 3):
+            if a.shape[ax] > 1:
+                lo_ = [slice(None)] * 4; hi_ = [slice(None)] * 4
+                lo_[ax] = slice(0, -1); hi_[ax] = slice(1, None)
+                a = f(a[tuple(lo_)], a[tuple(hi_)])
+        return a
+    x0, x1, y0, y1 = cells(px, np.minimum), cells(px, np.maximum), cells(py, np.minimum), cells(py, np.maximum)
+    boxes = np.stack([px.reshape(ncam, -1).min(1), py.reshape(ncam, -1).min(1), px.reshape(ncam, -1).max(1), py.reshape(ncam, -1).max(1)], 1)
+    lo = np.full((ncam, hs), np.iinfo(np.int32).max, np.int64)
+    hi = np.full((ncam, hs), -1, np.int64)
+    for c in range(ncam):
+        for a, b, r0, r1 in zip(x0[c].ravel(), x1[c].ravel(), y0[c].ravel(), y1[c].ravel()):
+            r0, r1 = max(r0, 0), min(r1, hs - 1)
+            lo[c, r0:r1 + 1] = np.minimum(lo[c, r0:r1 + 1], a)
+            hi[c, r0:r1 + 1] = np.maximum(hi[c, r0:r1 + 1], b)
+    return boxes.astype(np.int32), lo, hi
+
+
 def gather_mean(heatmaps_padded, idx):
     """index_select + camera mean (repro_layer.py:97-105). heatmaps_padded [ncam,K,hs,hs] -> [K,G,G,G]."""
     hm = _f32(heatmaps_padded)

@@ -176,6 +176,16 @@ def test_forward_host_uploads_only_the_pixel_boxes():
     assert np.array_equal(bx2.cpu().numpy(), boxes)
     sp = spans.cpu().numpy()
     lo, hi = sp[..., 0], -sp[..., 1]
+    # ... and exactly the oracle's (oracle.pixel_boxes_and_row_spans on the oracle's coarse projections)
+    from oracle import hybridnet_oracle as O
+    hn = [t.numpy() for t in host]
+    for b in range(5):
+        _, ca, cb = O.reproject_indices(hn[1][b], hn[2][b], hn[3][b], hn[4][b], hn[5][b], net.G, float(net.spacing), hs, return_coarse=True)
+        ob, olo, ohi = O.pixel_boxes_and_row_spans(ca, cb, hs)
+        assert np.array_equal(ob, np.stack([boxes[b, :, 0], boxes[b, :, 1], -boxes[b, :, 2], -boxes[b, :, 3]], 1))
+        rows = ohi >= olo
+        assert np.array_equal(rows, hi[b] >= lo[b])
+        assert np.array_equal(olo[rows], lo[b][rows]) and np.array_equal(ohi[rows], hi[b][rows])
     span_px = box_px = 0
     for b in range(5):
         for c in range(sh.ncam):

@@ -78,3 +78,26 @@ def test_pad_matches_reference_pad(oracle):
     p = oracle.pad_heatmaps(a)
     assert p.shape == (2, 3, 6, 6) and p[:, :, 0].sum() == 0 and p[:, :, :, -1].sum() == 0
     assert np.array_equal(p[:, :, 1:-1, 1:-1], a)
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_row_spans_hold_every_reference_index(oracle, name):
+    """oracle.pixel_boxes_and_row_spans (what jhn_heatmap_boxes / jhn_heatmap_spans compute on the GPU): the indices pinned above
+    by the reference's own sha all fall inside the per-row column spans, the spans are no wider than the boxes, and the boxes
+    are the spans' hull."""
+    sh, x, g = load_case(name)
+    idx, ca, cb = oracle.reproject_indices(x["c3"], x["chm"], x["cam"], x["intr"], x["dist"], sh.G, sh.spacing, sh.hs,
+                                           return_coarse=True)
+    boxes, lo, hi = oracle.pixel_boxes_and_row_spans(ca, cb, sh.hs)
+    span_px = box_px = 0
+    for c in range(sh.ncam):
+        xx, yy = idx[c].ravel() % sh.hs, idx[c].ravel() // sh.hs
+        assert (xx >= lo[c][yy]).all() and (xx <= hi[c][yy]).all()
+        rows = hi[c] >= lo[c]
+        x0, y0, x1, y1 = boxes[c]
+        assert np.flatnonzero(rows).min() == y0 and np.flatnonzero(rows).max() == y1 and rows[y0:y1 + 1].all()
+        assert lo[c][rows].min() == x0 and hi[c][rows].max() == x1
+        assert xx.min() >= x0 and xx.max() <= x1 and yy.min() >= y0 and yy.max() <= y1
+        span_px += int((hi[c] - lo[c] + 1)[rows].sum())
+        box_px += int((x1 - x0 + 1) * (y1 - y0 + 1))
+    assert span_px <= box_px
