@@ -584,7 +584,7 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
     const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < GS_SLOTS; ++i) { mbar_init(smem_u32(full + i), GS_LANE_ARRIVE ? 32 : 1); mbar_init(smem_u32(empty + i), 4); }
+        for (int i = 0; i < GS_SLOTS; ++i) { mbar_init(smem_u32(full + i), GS_LANE_ARRIVE ? 32 : 1); mbar_init(smem_u32(empty + i), GS_LANE_ARRIVE ? 128 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -797,8 +797,10 @@ gather_stream_kernel(const __half *__restrict__ hm, const float2 *__restrict__ c
                         for (int i = 0; i < 4; ++i) acc[v][4 * g + i] = __hadd2(acc[v][4 * g + i], *reinterpret_cast<const __half2 *>(&ww[i]));
                     }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(empty + s));
+            // release of the slot and of the older header: with GS_LANE_ARRIVE every lane of the four gather warps arrives itself
+            // (count 128), i.e. each lane's own reads precede its own arrive — the form racecheck can follow
+            if (GS_LANE_ARRIVE) mbar_arrive(smem_u32(empty + s));
+            else { __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(empty + s)); }
             if (++s == GS_SLOTS) { s = 0; ph ^= 1u; hsel ^= GS_SLOTS; }
         }
 

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+bash tools/gpu_check.sh r2_run74
+timeout -s KILL 420 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gpu_tensorcore.py tests/test_gpu_center.py tests/test_gpu_ingest.py -m gpu -q --timeout 400 -k "hybrid3d_bf16_end_to_end or fused_head_argmax or center_locate or crop or efftrack or pull_heatmap_spans or (tc_layer and 5-12-1)" > gpurun_out/r2_run74_racecheck.log 2>&1
+grep -E "RACECHECK SUMMARY|passed|failed|Error: Race" gpurun_out/r2_run74_racecheck.log | sed -E 's/\+0x[0-9a-f]+//g' | sort | uniq -c | tail -8
