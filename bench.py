@@ -612,10 +612,12 @@ def main():
     # Upload strategy (HybridNet3D.forward_host_async): "hybrid:0.6" = the copy engine moves 40 % of every chunk's per-camera pixel
     # boxes (strided DMA, bound by rows per second), the pull kernel reads the other 60 % straight out of the pinned host tensor
     # (bound by the link), both at once; chunk = the whole batch.  JHN_E2E_UPLOAD=dma JHN_E2E_CHUNK=8 is the copy-engine-only path.
-    # Up to 4 ranks per host; with 8 the ranks' transfers together hit the host's memory / PCIe fabric (~190 GB/s on this pool's
-    # boxes) and the copy engine alone is the more frugal client there: 8 GPUs 35.1 k frame-sets/s with "dma" against 31.8 k with
-    # the hybrid, 4 GPUs 25.5 k against 27.5 k (profiles/r02_run64_8gpu_*.json, r02_run66_4gpu_*.json).
-    e2e_upload = os.environ.get("JHN_E2E_UPLOAD", "hybrid:0.6" if precision == "bf16" and world <= 4 else "dma")
+    # Up to 4 ranks per host.  With 8 the ranks' transfers together hit the host's memory / PCIe fabric (~190 GB/s on this pool's
+    # boxes): bytes decide there, so every image is pulled as its per-row column spans (jhn_heatmap_spans, 22 % fewer bytes than the
+    # boxes; "hybrid-spans:1.0").  8 GPUs end to end: 40.8 k frame-sets/s, against 35.1 k with the copy engine alone and 31.8 k with the
+    # box hybrid; 4 GPUs: 27.5 k with the box hybrid, 25.5 k with the copy engine (profiles/r02_run64_8gpu_*.json,
+    # r02_run66_4gpu_*.json, r02_run78_8gpu_spans.txt).  On one GPU computing the spans costs more than the link gains.
+    e2e_upload = os.environ.get("JHN_E2E_UPLOAD", "dma" if precision != "bf16" else "hybrid:0.6" if world <= 4 else "hybrid-spans:1.0")
     e2e_chunk = int(os.environ.get("JHN_E2E_CHUNK", str(B) if e2e_upload.startswith("hybrid") else "8"))
     # Steps are pipelined, as a prediction loop with a prefetching loader runs them: up to `e2e_ahead` later steps are submitted
     # (forward_host_async: their uploads queue behind the running step's on the copy / pull streams) before a step's result is
@@ -646,8 +648,10 @@ def main():
     e2e = dict(value=world * B * K_steps / e2e_s, unit="frame-sets/s", h2d_bytes_per_step=int(h2d),
                d2h_bytes_per_step=int(d2h), ms_per_step=1e3 * e2e_s / K_steps,
                heatmap_format="fp16 channels-last (JHN_HM_F16_CL)" if precision == "bf16" else "fp32 planar",
-               upload="per-camera pixel boxes of the voxel grid only (jhn_heatmap_boxes; %s: jhn_upload_heatmap_boxes = copy engine, "
-                      "jhn_pull_heatmap_boxes = kernel reading the pinned host tensor), chunk %d, up to %d steps submitted ahead" % (e2e_upload, e2e_chunk, e2e_ahead))
+               upload="only the pixels of each camera's map that the voxel grid projects to (%s; dma = jhn_heatmap_boxes + jhn_upload_heatmap_boxes, "
+                      "copy engine; hybrid:f = a fraction f of the images by jhn_pull_heatmap_boxes, a kernel reading the pinned host tensor; "
+                      "hybrid-spans:f = those by jhn_heatmap_spans + jhn_pull_heatmap_spans, per-row column spans), chunk %d, up to %d steps "
+                      "submitted ahead" % (e2e_upload, e2e_chunk, e2e_ahead))
 
     # ---- B=1 latency (the reference's predictor runs one frame set per call): eager launches vs CUDA-graph replay ----
     latency = None
