@@ -314,7 +314,7 @@ class HybridNet3D(nn.Module):
                     pulled.zero_()
                 small = torch.cuda.Event()
                 small.record(aux)
-            if roi in ("dma", "hybrid"):
+            if roi == "dma" or (roi == "hybrid" and pull_frac < 1.0):
                 small.synchronize()                      # 1.5 KB back: the host needs the boxes to describe the strided copies
             copy_stream.wait_event(small)
             main.wait_event(small)
